@@ -1,0 +1,190 @@
+/*
+ * olfnav_b200.h — C ABI of the B200-native POMDP core for PimLb/olfactory-navigation.
+ *
+ * The reference has no FFI layer: its hot path is Python calling the third-party `pomdp_toolkit`
+ * (reference requirements.txt:7).  Each entry point below replaces one `pomdp_toolkit` call (or one
+ * in-repo per-step function) that the reference makes; the call site is cited as
+ * `file:line` relative to /root/reference/olfactory_navigation/.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*;
+ *   - every pointer marked [dev] is device memory owned by the CALLER (e.g. a torch tensor's
+ *     data_ptr()); [host] pointers are host memory read synchronously during the call;
+ *   - all work is enqueued on `stream`; no call synchronises the device unless it says so;
+ *   - every function returns an olfnav_status; olfnav_last_error() gives a message (per thread);
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns
+ *     OLFNAV_ERR_CUDA.
+ *
+ * Belief layout in HBM ("padded grid rows")
+ *   A belief over the H x W grid is stored as H rows of Wp = olfnav_padded_width(W) floats
+ *   (W rounded up to a multiple of 4, padding columns always 0), i.e. Sp = H*Wp floats per agent,
+ *   agents `ld` floats apart (ld >= Sp, ld % 4 == 0).  State s = y*W + x of the reference
+ *   (agents/model_based_util/environment_converter.py:43,111,118) lives at y*Wp + x.
+ *   Beliefs are stored UNNORMALISED with a per-agent scale: b_true[n,:] = b[n,:] * scale[n]
+ *   (deferred normalisation; the argmax of b.alpha is scale invariant).
+ *   Alpha vectors use the same padded state indexing.
+ */
+#ifndef OLFNAV_B200_H
+#define OLFNAV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLFNAV_ABI_VERSION 1
+#define OLFNAV_MAX_ACTIONS 16
+#define OLFNAV_MAX_OBSERVATIONS 32
+
+typedef enum {
+    OLFNAV_OK = 0,
+    OLFNAV_ERR_INVALID = 1,      /* bad argument */
+    OLFNAV_ERR_CUDA = 2,         /* CUDA runtime error (message in olfnav_last_error) */
+    OLFNAV_ERR_UNSUPPORTED = 3,  /* valid request outside what the kernels cover */
+    OLFNAV_ERR_NOMEM = 4
+} olfnav_status;
+
+/* environment.py:711-769 boundary conditions */
+typedef enum {
+    OLFNAV_BOUNDARY_STOP = 0,            /* clip both axes ('stop', 'clip') */
+    OLFNAV_BOUNDARY_WRAP = 1,            /* wrap both axes */
+    OLFNAV_BOUNDARY_WRAP_VERTICAL = 2,   /* wrap rows (y), clip columns */
+    OLFNAV_BOUNDARY_WRAP_HORIZONTAL = 3  /* wrap columns (x), clip rows */
+} olfnav_boundary;
+
+typedef struct olfnav_model olfnav_model;      /* POMDP tables on one device   */
+typedef struct olfnav_alphas olfnav_alphas;    /* value function on one device */
+typedef struct olfnav_env olfnav_env;          /* stepping environment on one device */
+
+int         olfnav_abi_version(void);
+const char* olfnav_last_error(void);
+int         olfnav_padded_width(int W);                 /* Wp */
+int64_t     olfnav_padded_states(int H, int W);         /* Sp = H * Wp */
+
+/* ------------------------------------------------------------------------------------------------
+ * Model  — replaces pomdp_toolkit.POMDP(...) built at
+ *          agents/model_based_util/environment_converter.py:125-133 (grid model of exact_converter).
+ *   moves        [host] A x 2 (dy, dx), |dy|,|dx| <= 1            (agent.py:239-250)
+ *   obs_table    [host] S x A x O float64, P(o | arrive s', a)    (environment_converter.py:77-94)
+ *   end_mask     [host] S bytes, 1 = end state                    (environment_converter.py:44-45)
+ *   start        [host] S float64 start probabilities             (environment_converter.py:132)
+ * Rewards follow the toolkit default: r_a(s) = 1 if R_a(s) is an end state.
+ * ---------------------------------------------------------------------------------------------- */
+int  olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O,
+                         const int32_t* moves, int boundary,
+                         const double* obs_table, const uint8_t* end_mask, const double* start);
+void olfnav_model_destroy(olfnav_model* m);
+int  olfnav_model_dims(const olfnav_model* m, int* H, int* W, int* Wp, int* A, int* O);
+
+/* Move a dense reference-layout array (n x S, state-major rows) into / out of the padded layout.
+ * dense_f64 / dense_f32: exactly one non-NULL.  `scale` may be NULL (treated as 1). */
+int olfnav_pack_rows(const olfnav_model* m, const double* dense_f64, const float* dense_f32,      /* [dev] n x S */
+                     float* padded, int64_t ld, int64_t n, void* stream);                       /* [dev] */
+int olfnav_unpack_rows(const olfnav_model* m, const float* padded, int64_t ld, int64_t n,
+                       const float* scale,                                                      /* [dev] n or NULL */
+                       double* dense_f64, float* dense_f32, void* stream);                      /* [dev] n x S */
+
+/* ------------------------------------------------------------------------------------------------
+ * Beliefs — BeliefSet(model, [Belief(model) for _ in range(n)])  agents/pbvi_agent.py:717,
+ *           agents/infotaxis_agent.py:232
+ * ---------------------------------------------------------------------------------------------- */
+int olfnav_belief_init(const olfnav_model* m, float* b, int64_t ld, int64_t n, float* scale, void* stream);
+
+/* BeliefSet.update(actions, observations, raise_on_impossible_belief=False, use_reachability=True,
+ *                  return_provenance=True)      agents/pbvi_agent.py:783-787, agents/infotaxis_agent.py:335-339
+ * For i in [0,n):  u = O[., a_i, o_i] * push_{a_i}( b_in[src_i,:] * scale_in[src_i] );  Z = sum(u)
+ *                  b_out[dst_i,:] = u ; scale_out[dst_i] = Z > 0 ? 1/Z : 0 ; ok[i] = Z > 0
+ * src_rows / dst_rows may be NULL (identity).  In place (b_out == b_in) is allowed iff
+ * src_i == dst_i for every i.  Writing dst_i = i with src_i = surviving rows compacts for free.
+ * `ok` replaces the provenance array: ok[i] <=> row i is in provenance[:,0]. */
+int olfnav_belief_step(const olfnav_model* m,
+                       const float* b_in, float* b_out, int64_t ld, int64_t n,
+                       const int32_t* act, const int32_t* obs,          /* [dev] n */
+                       const int32_t* src_rows, const int32_t* dst_rows,/* [dev] n or NULL */
+                       const float* scale_in, float* scale_out,         /* [dev] */
+                       uint8_t* ok,                                     /* [dev] n */
+                       void* stream);
+
+/* Belief compaction — `belief_array[~kill]`, agents/pbvi_agent.py:810-811, agents/infotaxis_agent.py:362-363.
+ * dst[i,:] = src[src_rows[i],:] and scale_dst[i] = scale_src[src_rows[i]] for i in [0,n); src != dst. */
+int olfnav_copy_rows(const float* src, float* dst, int64_t ld, int64_t row_len,
+                     const int32_t* src_rows, const float* scale_src, float* scale_dst, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Value function — ValueFunction(model, alpha_vectors, action_list)  agents/pbvi_agent.py:692
+ *   alpha   [dev] G x ld_alpha floats in the padded state layout (padding columns ignored)
+ *   actions [dev] G int32
+ * The handle keeps its own packed copy (split-precision operand planes for the tensor-core path).
+ * ---------------------------------------------------------------------------------------------- */
+int  olfnav_alphas_create(olfnav_alphas** out, const olfnav_model* m, const float* alpha, int64_t ld_alpha,
+                          const int32_t* actions, int G, void* stream);
+void olfnav_alphas_destroy(olfnav_alphas* a);
+
+/* ValueFunction.evaluate_at(BeliefSet) -> (values, actions)      agents/pbvi_agent.py:741
+ * value[i] = scale[i] * max_g b[i,:].alpha_g ; arg[i] = first argmax ; action[i] = actions[arg[i]].
+ * Any of value/arg/action may be NULL.  `path`: 0 = auto, 1 = FP32 SIMT kernel,
+ * 2 = tcgen05 tensor-core kernel (3xTF32 split precision). */
+int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a,
+                    const float* b, int64_t ld, int64_t n, const float* scale,
+                    float* value, int32_t* arg, int32_t* action, int path, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Infotaxis — Infotaxis_Agent.choose_action           agents/infotaxis_agent.py:244-301
+ * action[i] = first argmax_a [ H(b_i) - sum_o P(o|b_i,a) H(b_i^{a,o}) ]; dH (n x A) optional.
+ * ---------------------------------------------------------------------------------------------- */
+int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
+                            int32_t* action, float* dH, void* stream);
+
+/* BeliefSet.entropies   agents/infotaxis_agent.py:257 : H[i] = -sum b log b of the normalised row */
+int olfnav_entropies(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
+                     float* H_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PBVI backup — inside pomdp_toolkit.solvers.<X>.solve        agents/fsvi_agent.py:201-224 (+7 siblings)
+ *   gamma_build : Gamma[a][o][g][:] = gamma * O_o(R_a(.)) * alpha_g(R_a(.))      (A*O*G x ld)
+ *   select      : g*[b,a,o] = argmax_g b.Gamma_{a,o}^g ; a*[b] = argmax_a ( b.r_a + sum_o max_g ... )
+ *   assemble    : alpha_new[b,:] = r_{a*} + sum_o Gamma_{a*,o}^{g*[b,a*,o]}
+ * ---------------------------------------------------------------------------------------------- */
+int olfnav_backup_gamma(const olfnav_model* m, const float* alpha, int64_t ld_alpha, int G, float discount,
+                        float* gamma_ao, int64_t ld_gamma, void* stream);
+int olfnav_backup_select(const olfnav_model* m, const float* b, int64_t ld, int64_t n_beliefs, const float* scale,
+                         const float* gamma_ao, int64_t ld_gamma, int G,
+                         int32_t* best_g /* n x A x O */, int32_t* best_a /* n */, float* best_value /* n */,
+                         int path, void* stream);
+int olfnav_backup_assemble(const olfnav_model* m, const float* gamma_ao, int64_t ld_gamma, int G,
+                           const int32_t* best_g, const int32_t* best_a, int64_t n_beliefs,
+                           float* alpha_new, int64_t ld_new, void* stream);
+
+/* solvers.VI.solve sweep      agents/qmdp_agent.py:145-153
+ * Q_out[a][s] = r_a(s) + discount * max_a' Q_in[a'][R_a(s)] ; max_change = max_s |V_out - V_in|.
+ * float64 on purpose: V grows to 1/(1-discount) while the stopping rule looks at changes of 1e-4. */
+int olfnav_vi_sweep(const olfnav_model* m, const double* Q_in, double* Q_out, int64_t ld_q, double discount,
+                    double* max_change /* [dev] 1 double, atomically maxed; caller zeroes */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Environment stepping — environment.py:711-769 (move), :554-652 (get_observation),
+ *                        :655-680 (source_reached); agent.py:375-439 (discretize_observations)
+ *   data [host] T x h x w float64 odor frames; margins (my, mx) = low margins of the data zone.
+ * ---------------------------------------------------------------------------------------------- */
+int  olfnav_env_create(olfnav_env** out, int device, int H, int W, int boundary,
+                       const double* data, int T, int h, int w, int margin_y, int margin_x,
+                       double source_y, double source_x, double source_radius);
+void olfnav_env_destroy(olfnav_env* e);
+
+/* One simulation step for n agents (simulation.py:1457-1466 + agent.py:401-439):
+ *   pos <- move(pos, moves[act]); odor = data[(time_shift + step) % T, pos - margins] or 0 outside;
+ *   reached = |pos - source|^2 <= r^2; obs_id = threshold bin of odor, or n_bins when reached.
+ *   thresholds [dev] n_thr float64 ascending, thresholds[0] = -inf, thresholds[n_thr-1] = +inf. */
+int olfnav_env_step(const olfnav_env* e, int64_t n,
+                    int32_t* pos /* [dev] n x 2 (y, x), in/out */, const int32_t* act /* [dev] n */,
+                    const int32_t* moves /* [dev] A x 2 */, const int64_t* time_shift /* [dev] n */, int64_t step,
+                    const double* thresholds, int n_thr,
+                    double* odor /* [dev] n */, int32_t* obs_id /* [dev] n */, uint8_t* reached /* [dev] n */,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLFNAV_B200_H */

@@ -1,0 +1,122 @@
+// Shared device/host helpers for the olfnav_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/olfnav_b200.h"
+
+#ifndef OLFNAV_MAX_ACTIONS
+#error "header not found"
+#endif
+
+// ---- error plumbing (never throw across the C ABI) ------------------------------------------------
+void olfnav_set_error(const char* fmt, ...);
+
+#define OLF_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            olfnav_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return OLFNAV_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+
+#define OLF_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            olfnav_set_error(__VA_ARGS__);                                                     \
+            return OLFNAV_ERR_INVALID;                                                         \
+        }                                                                                      \
+    } while (0)
+
+#define OLF_LAUNCH_CHECK()                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            olfnav_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return OLFNAV_ERR_CUDA;                                                            \
+        }                                                                                      \
+    } while (0)
+
+// ---- grid geometry shared by every kernel ------------------------------------------------------------
+struct Geom {
+    int H, W, Wp, W4;      // Wp = W rounded up to 4, W4 = Wp / 4 (float4 per grid row)
+    int S, Sp;             // S = H*W (reference states), Sp = H*Wp (padded)
+    int A, O;
+    int wrap_y, wrap_x;    // boundary per axis: 1 = wrap, 0 = clip ("stop")
+    int obs_per_action;    // 1: observation table differs per action (layered); 0: shared
+    unsigned div_w4;       // ceil(2^32 / W4): q = umulhi(n, div_w4) for n < 2^16
+    int moves[OLFNAV_MAX_ACTIONS][2];   // (dy, dx)
+};
+
+struct olfnav_model {
+    int device;
+    Geom g;
+    float* obs;        // [A_eff][O][Sp]   P(o | arrive s'), zero in padding columns
+    float* obs_ent;    // [A_eff][Sp]      C(s') = sum_o O_o(s') log O_o(s')   (infotaxis)
+    float* reward;     // [A][Sp]          r_a(s) = 1[R_a(s) in end states]
+    float* start;      // [Sp]
+    uint8_t* end_mask; // [Sp]
+    int sm_count;
+};
+
+struct olfnav_alphas {
+    int device;
+    int G, Gp;           // Gp = G rounded up to the tensor-core tile granularity
+    int64_t ld;          // row stride (floats) of the planes, multiple of 32
+    float* hi;           // [Gp][ld]  tf32-representable high part (low 13 mantissa bits zero)
+    float* lo;           // [Gp][ld]  alpha - hi, also tf32-representable
+    float* full;         // [Gp][ld]  fp32 copy (SIMT path)
+    int32_t* actions;    // [G]
+};
+
+struct olfnav_env {
+    int device;
+    int H, W, wrap_y, wrap_x;
+    int T, h, w, my, mx;
+    double sy, sx, r2;
+    double* data;      // [T][h][w]
+};
+
+// ---- small device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in every thread.  `red` holds >= 33 floats.
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float t = (lane < THREADS / 32) ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    float r = red[32];
+    __syncthreads();
+    return r;
+}
+
+static inline int olf_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

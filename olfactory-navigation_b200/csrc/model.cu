@@ -1,0 +1,173 @@
+// Model / value-function / environment handles and error plumbing of the C ABI.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+void olfnav_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* olfnav_last_error(void) { return g_err; }
+extern "C" int olfnav_abi_version(void) { return OLFNAV_ABI_VERSION; }
+extern "C" int olfnav_padded_width(int W) { return (W + 3) & ~3; }
+extern "C" int64_t olfnav_padded_states(int H, int W) { return (int64_t)H * ((W + 3) & ~3); }
+
+static int set_boundary(int boundary, int* wrap_y, int* wrap_x) {
+    switch (boundary) {
+        case OLFNAV_BOUNDARY_STOP: *wrap_y = 0; *wrap_x = 0; return 0;
+        case OLFNAV_BOUNDARY_WRAP: *wrap_y = 1; *wrap_x = 1; return 0;
+        case OLFNAV_BOUNDARY_WRAP_VERTICAL: *wrap_y = 1; *wrap_x = 0; return 0;
+        case OLFNAV_BOUNDARY_WRAP_HORIZONTAL: *wrap_y = 0; *wrap_x = 1; return 0;
+        default: return -1;
+    }
+}
+
+static inline int bmove(int v, int d, int n, int wrap) {
+    v += d;
+    if (wrap) { if (v < 0) v += n; if (v >= n) v -= n; }
+    else { if (v < 0) v = 0; if (v > n - 1) v = n - 1; }
+    return v;
+}
+
+extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O,
+                                   const int32_t* moves, int boundary,
+                                   const double* obs_table, const uint8_t* end_mask, const double* start) {
+    OLF_REQUIRE(out && moves && obs_table && end_mask && start, "model_create: null argument");
+    OLF_REQUIRE(H >= 1 && W >= 1 && (int64_t)H * W < (1LL << 30), "model_create: bad grid %d x %d", H, W);
+    OLF_REQUIRE(A >= 1 && A <= OLFNAV_MAX_ACTIONS, "model_create: A must be in [1,%d]", OLFNAV_MAX_ACTIONS);
+    OLF_REQUIRE(O >= 1 && O <= OLFNAV_MAX_OBSERVATIONS, "model_create: O must be in [1,%d]", OLFNAV_MAX_OBSERVATIONS);
+    int wy, wx;
+    OLF_REQUIRE(set_boundary(boundary, &wy, &wx) == 0, "model_create: unknown boundary %d", boundary);
+    for (int a = 0; a < A; ++a) {
+        if (abs(moves[2 * a]) > 1 || abs(moves[2 * a + 1]) > 1) {
+            olfnav_set_error("model_create: move %d = (%d,%d): only unit steps are supported", a, moves[2 * a], moves[2 * a + 1]);
+            return OLFNAV_ERR_UNSUPPORTED;
+        }
+    }
+    int ndev = 0;
+    OLF_CUDA(cudaGetDeviceCount(&ndev));
+    OLF_REQUIRE(device >= 0 && device < ndev, "model_create: device %d of %d", device, ndev);
+    OLF_CUDA(cudaSetDevice(device));
+
+    olfnav_model* m = new (std::nothrow) olfnav_model();
+    if (!m) { olfnav_set_error("model_create: out of host memory"); return OLFNAV_ERR_NOMEM; }
+    memset(m, 0, sizeof(*m));
+    m->device = device;
+    Geom& g = m->g;
+    g.H = H; g.W = W; g.Wp = (W + 3) & ~3; g.W4 = g.Wp / 4; g.S = H * W; g.Sp = H * g.Wp;
+    g.A = A; g.O = O; g.wrap_y = wy; g.wrap_x = wx;
+    g.div_w4 = (g.W4 > 1) ? (unsigned)(((1ULL << 32) + g.W4 - 1) / g.W4) : 0u;
+    for (int a = 0; a < A; ++a) { g.moves[a][0] = moves[2 * a]; g.moves[a][1] = moves[2 * a + 1]; }
+
+    // Is the observation table action dependent?  (layered environments only; environment_converter.py:79-85)
+    const int S = g.S, Sp = g.Sp;
+    int per_action = 0;
+    for (int s = 0; s < S && !per_action; ++s)
+        for (int a = 1; a < A && !per_action; ++a)
+            for (int o = 0; o < O; ++o)
+                if (obs_table[((size_t)s * A + a) * O + o] != obs_table[((size_t)s * A) * O + o]) { per_action = 1; break; }
+    g.obs_per_action = per_action;
+    const int Aeff = per_action ? A : 1;
+
+    std::vector<float> h_obs((size_t)Aeff * O * Sp, 0.f), h_ent((size_t)Aeff * Sp, 0.f), h_rew((size_t)A * Sp, 0.f), h_start(Sp, 0.f);
+    std::vector<uint8_t> h_end(Sp, 0);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int s = y * W + x, sp = y * g.Wp + x;
+            h_start[sp] = (float)start[s];
+            h_end[sp] = end_mask[s] ? 1 : 0;
+            for (int a = 0; a < Aeff; ++a) {
+                double c = 0.0;
+                for (int o = 0; o < O; ++o) {
+                    const double pr = obs_table[((size_t)s * A + a) * O + o];
+                    h_obs[((size_t)a * O + o) * Sp + sp] = (float)pr;
+                    if (pr > 0.0) c += pr * log(pr);
+                }
+                h_ent[(size_t)a * Sp + sp] = (float)c;
+            }
+            for (int a = 0; a < A; ++a) {
+                const int y2 = bmove(y, g.moves[a][0], H, wy), x2 = bmove(x, g.moves[a][1], W, wx);
+                h_rew[(size_t)a * Sp + sp] = end_mask[y2 * W + x2] ? 1.f : 0.f;
+            }
+        }
+
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** dptr, const void* src, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(dptr, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void**)&m->obs, h_obs.data(), h_obs.size() * sizeof(float));
+    up((void**)&m->obs_ent, h_ent.data(), h_ent.size() * sizeof(float));
+    up((void**)&m->reward, h_rew.data(), h_rew.size() * sizeof(float));
+    up((void**)&m->start, h_start.data(), h_start.size() * sizeof(float));
+    up((void**)&m->end_mask, h_end.data(), h_end.size());
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        olfnav_set_error("model_create: %s", cudaGetErrorString(e));
+        olfnav_model_destroy(m);
+        return OLFNAV_ERR_CUDA;
+    }
+    *out = m;
+    return OLFNAV_OK;
+}
+
+extern "C" void olfnav_model_destroy(olfnav_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
+    delete m;
+}
+
+extern "C" int olfnav_model_dims(const olfnav_model* m, int* H, int* W, int* Wp, int* A, int* O) {
+    OLF_REQUIRE(m, "model_dims: null model");
+    if (H) *H = m->g.H;
+    if (W) *W = m->g.W;
+    if (Wp) *Wp = m->g.Wp;
+    if (A) *A = m->g.A;
+    if (O) *O = m->g.O;
+    return OLFNAV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" int olfnav_env_create(olfnav_env** out, int device, int H, int W, int boundary,
+                                 const double* data, int T, int h, int w, int margin_y, int margin_x,
+                                 double source_y, double source_x, double source_radius) {
+    OLF_REQUIRE(out && data, "env_create: null argument");
+    OLF_REQUIRE(H >= 1 && W >= 1 && T >= 1 && h >= 1 && w >= 1, "env_create: bad sizes");
+    int wy, wx;
+    OLF_REQUIRE(set_boundary(boundary, &wy, &wx) == 0, "env_create: unknown boundary %d", boundary);
+    OLF_CUDA(cudaSetDevice(device));
+    olfnav_env* e = new (std::nothrow) olfnav_env();
+    if (!e) { olfnav_set_error("env_create: out of host memory"); return OLFNAV_ERR_NOMEM; }
+    memset(e, 0, sizeof(*e));
+    e->device = device; e->H = H; e->W = W; e->wrap_y = wy; e->wrap_x = wx;
+    e->T = T; e->h = h; e->w = w; e->my = margin_y; e->mx = margin_x;
+    e->sy = source_y; e->sx = source_x; e->r2 = source_radius * source_radius;
+    const size_t bytes = (size_t)T * h * w * sizeof(double);
+    cudaError_t ce = cudaMalloc((void**)&e->data, bytes);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->data, data, bytes, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        olfnav_set_error("env_create: %s", cudaGetErrorString(ce));
+        olfnav_env_destroy(e);
+        return OLFNAV_ERR_CUDA;
+    }
+    *out = e;
+    return OLFNAV_OK;
+}
+
+extern "C" void olfnav_env_destroy(olfnav_env* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->data);
+    delete e;
+}

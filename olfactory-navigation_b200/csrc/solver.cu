@@ -1,0 +1,248 @@
+// Environment stepping, MDP value iteration and the streaming halves of the PBVI backup.
+#include "common.cuh"
+#include "umma_gemm.cuh"
+
+int olf_segmax_simt(const float* b, int64_t ld, int64_t n, int K4, const float* M, int64_t ldM, int n_seg, int seg_len,
+                    float* out_val, int* out_arg, cudaStream_t st);
+
+namespace {
+
+__device__ __forceinline__ int bmove_dev(int v, int d, int n, int wrap) {
+    v += d;
+    if (wrap) { if (v < 0) v += n; if (v >= n) v -= n; }
+    else { v = max(0, min(n - 1, v)); }
+    return v;
+}
+
+// simulation.py:1457-1466 + agent.py:401-439, one thread per agent.
+__global__ void env_step_kernel(const olfnav_env e, int n, int* __restrict__ pos, const int* __restrict__ act,
+                                const int* __restrict__ moves, const long long* __restrict__ time_shift, long long step,
+                                const double* __restrict__ thr, int n_thr,
+                                double* __restrict__ odor, int* __restrict__ obs_id, unsigned char* __restrict__ reached) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = act[i];
+    // environment.py:711-769
+    const int y = bmove_dev(pos[2 * i], moves[2 * a], e.H, e.wrap_y);
+    const int x = bmove_dev(pos[2 * i + 1], moves[2 * a + 1], e.W, e.wrap_x);
+    pos[2 * i] = y;
+    pos[2 * i + 1] = x;
+    // environment.py:591 (time loops), :638-651 (0.0 outside the data zone)
+    long long t = (time_shift[i] + step) % e.T;
+    if (t < 0) t += e.T;
+    const int dyp = y - e.my, dxp = x - e.mx;
+    double v = 0.0;
+    if (dyp >= 0 && dyp < e.h && dxp >= 0 && dxp < e.w) v = e.data[((size_t)t * e.h + dyp) * e.w + dxp];
+    odor[i] = v;
+    // environment.py:655-680
+    const double ddy = (double)y - e.sy, ddx = (double)x - e.sx;
+    const bool hit = (ddy * ddy + ddx * ddx) <= e.r2;
+    reached[i] = hit ? 1 : 0;
+    // agent.py:420 bins [t_k, t_{k+1}); :437 goal id = number of bins
+    int id = -1;
+    for (int k = 0; k + 1 < n_thr; ++k)
+        if (v >= thr[k] && v < thr[k + 1]) { id = k; break; }
+    obs_id[i] = hit ? (n_thr - 1) : id;
+}
+
+// solvers.VI: Q_out[a][s] = r_a(s) + discount * max_a' Q_in[a'][R_a(s)]   (float64: V reaches 1/(1-gamma))
+__global__ void vi_sweep_kernel(const Geom g, const float* __restrict__ reward, const double* __restrict__ Qin,
+                                double* __restrict__ Qout, long long ldq, double discount, double* __restrict__ max_change) {
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    double change = 0.0;
+    if (sp < g.Sp) {
+        const int y = sp / g.Wp, x = sp - y * g.Wp;
+        if (x < g.W) {
+            double vin = -1e300, vout = -1e300;
+            for (int a = 0; a < g.A; ++a) vin = fmax(vin, Qin[a * ldq + sp]);
+            for (int a = 0; a < g.A; ++a) {
+                const int d = bmove_dev(y, g.moves[a][0], g.H, g.wrap_y) * g.Wp + bmove_dev(x, g.moves[a][1], g.W, g.wrap_x);
+                double vd = -1e300;
+                for (int a2 = 0; a2 < g.A; ++a2) vd = fmax(vd, Qin[a2 * ldq + d]);
+                const double q = (double)reward[(size_t)a * g.Sp + sp] + discount * vd;
+                Qout[a * ldq + sp] = q;
+                vout = fmax(vout, q);
+            }
+            change = fabs(vout - vin);
+        } else {
+            for (int a = 0; a < g.A; ++a) Qout[a * ldq + sp] = 0.0;
+        }
+    }
+    // non-negative doubles order like their bit patterns
+    for (int o = 16; o > 0; o >>= 1) change = fmax(change, __shfl_xor_sync(0xffffffffu, change, o));
+    if ((threadIdx.x & 31) == 0 && change > 0.0)
+        atomicMax(reinterpret_cast<unsigned long long*>(max_change), (unsigned long long)__double_as_longlong(change));
+}
+
+// Gamma[a][o][g][s] = discount * O_o(R_a(s)) * alpha_g(R_a(s))      (SURVEY App. B "Backup (pull)")
+__global__ void backup_gamma_kernel(const Geom g, const float* __restrict__ obs, const float* __restrict__ alpha, long long ld_alpha,
+                                    int G, float discount, float* __restrict__ out, long long ld_out) {
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gi = blockIdx.y, a = blockIdx.z;
+    if (sp >= ld_out) return;
+    const int y = sp / g.Wp, x = sp - y * g.Wp;
+    const bool real = sp < g.Sp && x < g.W;
+    int d = 0;
+    float av = 0.f;
+    if (real) {
+        d = bmove_dev(y, g.moves[a][0], g.H, g.wrap_y) * g.Wp + bmove_dev(x, g.moves[a][1], g.W, g.wrap_x);
+        av = discount * alpha[(long long)gi * ld_alpha + d];
+    }
+    const float* ob = obs + (size_t)(g.obs_per_action ? a : 0) * g.O * g.Sp;
+    for (int o = 0; o < g.O; ++o) {
+        const float v = real ? av * ob[(size_t)o * g.Sp + d] : 0.f;
+        out[((long long)(a * g.O + o) * G + gi) * ld_out + sp] = v;
+    }
+}
+
+// best_a[b] = first argmax_a ( b.r_a + sum_o maxval[b,a,o] ), all in *scaled* (true belief) units.
+__global__ void backup_pick_kernel(int n, int A, int O, const float* __restrict__ scale, const float* __restrict__ seg_val,
+                                   const float* __restrict__ rew_val, int* __restrict__ best_a, float* __restrict__ best_value) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float best = -INFINITY;
+    int ba = 0;
+    for (int a = 0; a < A; ++a) {
+        float q = rew_val[i * A + a];
+        for (int o = 0; o < O; ++o) q += seg_val[(long long)i * A * O + a * O + o];
+        if (q > best) { best = q; ba = a; }
+    }
+    best_a[i] = ba;
+    if (best_value) best_value[i] = best * (scale ? scale[i] : 1.f);
+}
+
+// alpha_new[b][:] = r_{a*} + sum_o Gamma[a*][o][g*(b,a*,o)][:]
+__global__ void backup_assemble_kernel(const Geom g, const float* __restrict__ reward, const float* __restrict__ gamma_ao,
+                                       long long ld_gamma, int G, const int* __restrict__ best_g, const int* __restrict__ best_a,
+                                       float* __restrict__ out, long long ld_out) {
+    const long long b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    if (4 * c >= ld_out) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < g.Sp / 4) {
+        const int a = best_a[b];
+        acc = __ldg(reinterpret_cast<const float4*>(reward + (size_t)a * g.Sp) + c);
+        for (int o = 0; o < g.O; ++o) {
+            const int gi = best_g[(b * g.A + a) * g.O + o];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(gamma_ao + ((long long)(a * g.O + o) * G + gi) * ld_gamma) + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    *reinterpret_cast<float4*>(out + b * ld_out + 4 * (size_t)c) = acc;
+}
+
+__global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
+                                    float* __restrict__ hi, float* __restrict__ lo, long long ld) {
+    const long long r = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ld) return;
+    const float v = (r < rows && c < K) ? src[r * ld_src + c] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[r * ld + c] = h;
+    lo[r * ld + c] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+}
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" int olfnav_env_step(const olfnav_env* e, int64_t n, int32_t* pos, const int32_t* act, const int32_t* moves,
+                               const int64_t* time_shift, int64_t step, const double* thresholds, int n_thr,
+                               double* odor, int32_t* obs_id, uint8_t* reached, void* stream) {
+    OLF_REQUIRE(e && pos && act && moves && time_shift && thresholds && odor && obs_id && reached, "env_step: null argument");
+    OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL && n_thr >= 2, "env_step: bad n or n_thr");
+    if (n == 0) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(e->device));
+    env_step_kernel<<<olf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(*e, (int)n, pos, act, moves, (const long long*)time_shift,
+                                                                         (long long)step, thresholds, n_thr, odor, obs_id, reached);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+extern "C" int olfnav_vi_sweep(const olfnav_model* m, const double* Q_in, double* Q_out, int64_t ld_q, double discount,
+                               double* max_change, void* stream) {
+    OLF_REQUIRE(m && Q_in && Q_out && max_change && ld_q >= m->g.Sp, "vi_sweep: bad argument");
+    OLF_CUDA(cudaSetDevice(m->device));
+    vi_sweep_kernel<<<olf_div_up(m->g.Sp, 256), 256, 0, (cudaStream_t)stream>>>(m->g, m->reward, Q_in, Q_out, ld_q, discount, max_change);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+extern "C" int olfnav_backup_gamma(const olfnav_model* m, const float* alpha, int64_t ld_alpha, int G, float discount,
+                                   float* gamma_ao, int64_t ld_gamma, void* stream) {
+    OLF_REQUIRE(m && alpha && gamma_ao && G >= 1, "backup_gamma: bad argument");
+    OLF_REQUIRE(ld_alpha >= m->g.Sp && ld_gamma >= m->g.Sp && (ld_gamma % 4) == 0, "backup_gamma: bad leading dimension");
+    OLF_REQUIRE(G <= 65535, "backup_gamma: G too large");
+    OLF_CUDA(cudaSetDevice(m->device));
+    dim3 grid(olf_div_up(ld_gamma, 256), G, m->g.A);
+    backup_gamma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m->g, m->obs, alpha, ld_alpha, G, discount, gamma_ao, ld_gamma);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
+                                    const float* gamma_ao, int64_t ld_gamma, int G,
+                                    int32_t* best_g, int32_t* best_a, float* best_value, int path, void* stream) {
+    OLF_REQUIRE(m && b && gamma_ao && best_g && best_a, "backup_select: null argument");
+    OLF_REQUIRE(ld >= m->g.Sp && (ld % 4) == 0 && ld_gamma >= m->g.Sp && (ld_gamma % 4) == 0, "backup_select: bad leading dimension");
+    OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL && G >= 1 && path >= 0 && path <= 2, "backup_select: bad n, G or path");
+    if (n == 0) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int A = m->g.A, O = m->g.O, nseg = A * O;
+    if (path == 0) path = ((long long)G * nseg <= 64) ? 1 : 2;
+
+    float *seg_val = nullptr, *rew_val = nullptr;
+    int* rew_arg = nullptr;
+    OLF_CUDA(cudaMallocAsync((void**)&seg_val, (size_t)n * nseg * sizeof(float), st));
+    OLF_CUDA(cudaMallocAsync((void**)&rew_val, (size_t)n * A * sizeof(float), st));
+    OLF_CUDA(cudaMallocAsync((void**)&rew_arg, (size_t)n * A * sizeof(int), st));
+    int rc = OLFNAV_OK;
+    if (path == 1) {
+        rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, gamma_ao, ld_gamma, nseg, G, seg_val, best_g, st);
+    } else {
+        // split the Gamma rows into TF32 hi/lo planes with each (a,o) segment padded to a multiple of 16 rows
+        const int Gs = (G + 15) & ~15;
+        const long long ldp = (m->g.Sp + 31) & ~31;
+        float *hi = nullptr, *lo = nullptr;
+        OLF_CUDA(cudaMallocAsync((void**)&hi, (size_t)nseg * Gs * ldp * sizeof(float), st));
+        OLF_CUDA(cudaMallocAsync((void**)&lo, (size_t)nseg * Gs * ldp * sizeof(float), st));
+        for (int s = 0; s < nseg && rc == OLFNAV_OK; ++s) {
+            dim3 grid(olf_div_up(ldp, 256), Gs);
+            split_planes_kernel<<<grid, 256, 0, st>>>(gamma_ao + (long long)s * G * ld_gamma, ld_gamma, G, m->g.Sp,
+                                                      hi + (long long)s * Gs * ldp, lo + (long long)s * Gs * ldp, ldp);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: split launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        if (rc == OLFNAV_OK)
+            rc = olf_umma_segmax(b, ld, n, m->g.Sp, hi, lo, ldp, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
+        cudaFreeAsync(hi, st);
+        cudaFreeAsync(lo, st);
+    }
+    // b . r_a : A one-row segments (exact FP32)
+    if (rc == OLFNAV_OK) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, m->reward, m->g.Sp, A, 1, rew_val, rew_arg, st);
+    if (rc == OLFNAV_OK) {
+        backup_pick_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, A, O, scale, seg_val, rew_val, best_a, best_value);
+        if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: pick launch failed"); rc = OLFNAV_ERR_CUDA; }
+    }
+    cudaFreeAsync(seg_val, st);
+    cudaFreeAsync(rew_val, st);
+    cudaFreeAsync(rew_arg, st);
+    return rc;
+}
+
+extern "C" int olfnav_backup_assemble(const olfnav_model* m, const float* gamma_ao, int64_t ld_gamma, int G,
+                                      const int32_t* best_g, const int32_t* best_a, int64_t n, float* alpha_new, int64_t ld_new,
+                                      void* stream) {
+    OLF_REQUIRE(m && gamma_ao && best_g && best_a && alpha_new, "backup_assemble: null argument");
+    OLF_REQUIRE(ld_gamma >= m->g.Sp && (ld_gamma % 4) == 0 && ld_new >= m->g.Sp && (ld_new % 4) == 0, "backup_assemble: bad leading dimension");
+    if (n == 0) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(m->device));
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+        const int rows = (int)((n - r0 < 65535) ? (n - r0) : 65535);
+        dim3 grid(olf_div_up(ld_new / 4, 256), rows);
+        backup_assemble_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m->g, m->reward, gamma_ao, ld_gamma, G,
+                                                                       best_g + r0 * m->g.A * m->g.O, best_a + r0,
+                                                                       alpha_new + r0 * ld_new, ld_new);
+    }
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}

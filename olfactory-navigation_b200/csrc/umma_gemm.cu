@@ -1,0 +1,365 @@
+// tcgen05 / TMEM / TMA GEMM with FP32-accurate split precision (3xTF32) and a fused per-row segmented
+// max/argmax epilogue.  Serves
+//   * ValueFunction.evaluate_at   (reference agents/pbvi_agent.py:741):  beliefs (N x S) x alphas (S x G)
+//   * the PBVI backup contraction (inside solvers.*.solve, reference agents/fsvi_agent.py:201-224):
+//     beliefs (B x S) x Gamma_{a,o} (S x G*A*O), argmax over g inside every (a,o) segment.
+//
+// D (128 x BN, FP32, in TMEM) += A_hi·B_hi + A_lo·B_hi + A_hi·B_lo per K block of 32, where x_hi is x with the
+// low 13 mantissa bits cleared (exactly TF32) and x_lo = trunc_tf32(x - x_hi).  The dropped terms are
+// below 2^-21 |a||b|, which protects the argmax the same way an FP32 FMA chain does.
+//
+// Warp roles (384 threads, one CTA per SM, persistent over 128-row tiles of A):
+//   warp 0      TMA producer: A tile (raw FP32) + B_hi + B_lo tiles, 128B swizzle, mbarrier complete_tx
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32, tcgen05.commit frees stages
+//   warp 2      TMEM allocator
+//   warps 4-7   A transform: split the raw tile in place into hi (same buffer) and lo (second buffer)
+//   warps 8-11  epilogue: tcgen05.ld the accumulator, running segmented max/argmax in registers
+// Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
+#include "common.cuh"
+#include "umma_gemm.cuh"
+
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;          // rows of A per tile (UMMA M)
+constexpr int BK = 32;           // K per block: 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;        // K per tcgen05.mma.kind::tf32
+constexpr int NTHREADS = 384;
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
+
+struct GemmParams {
+    int n_rows, K, rows_b;
+    int n_seg, seg_len, seg_stride;
+    float* out_val;
+    int* out_arg;
+    int num_m_tiles, num_n_tiles, num_k_blocks;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("olfnav umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO = 1 (unused),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_tf32() {
+    // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int B_TILE_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-byte alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+    auto a_hi = [&](int s) { return base + s * L::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES; };
+    auto b_hi = [&](int s) { return base + s * L::STAGE_BYTES + 2 * A_TILE_BYTES; };
+    auto b_lo = [&](int s) { return base + s * L::STAGE_BYTES + 2 * A_TILE_BYTES + L::B_TILE_BYTES; };
+    const uint32_t bars = base + L::BAR_OFFSET;
+    auto bar_full = [&](int s) { return bars + 8 * s; };
+    auto bar_ready = [&](int s) { return bars + 8 * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8 * (2 * STAGES + s); };
+    auto bar_tfull = [&](int a) { return bars + 8 * (3 * STAGES + a); };
+    auto bar_tempty = [&](int a) { return bars + 8 * (3 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * (3 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBlo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 128); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int KB = p.num_k_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+                for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(bar_empty(s), ph ^ 1);
+                        mbar_expect_tx(bar_full(s), A_TILE_BYTES + 2 * L::B_TILE_BYTES);
+                        tma_load_2d(a_hi(s), &tmA, kb * BK, mt * BM, bar_full(s));
+                        tma_load_2d(b_hi(s), &tmBhi, kb * BK, nt * BN, bar_full(s));
+                        tma_load_2d(b_lo(s), &tmBlo, kb * BK, nt * BN, bar_full(s));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32<BN>();
+        uint32_t it = 0, tcount = 0;
+        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+            for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
+                const int acc = tcount & 1;
+                const uint32_t aph = (tcount >> 1) & 1;
+                mbar_wait(bar_tempty(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_ready(s), ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
+                        const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
+                            tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+                            tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+                        }
+                        tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
+                        if (kb == KB - 1) tc_commit(bar_tfull(acc));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== A transform: raw FP32 -> (hi in place, lo) =====================
+        const int t = threadIdx.x - 128;
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_full(s), ph);
+                    const uint32_t ah = a_hi(s), al = a_lo(s);
+#pragma unroll
+                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                        const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ah + off));
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                        l.x = __uint_as_float(__float_as_uint(v.x - h.x) & 0xffffe000u);
+                        l.y = __uint_as_float(__float_as_uint(v.y - h.y) & 0xffffe000u);
+                        l.z = __uint_as_float(__float_as_uint(v.z - h.z) & 0xffffe000u);
+                        l.w = __uint_as_float(__float_as_uint(v.w - h.w) & 0xffffe000u);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ah + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(al + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+                    mbar_arrive(bar_ready(s));
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue: segmented running max / argmax =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        uint32_t tcount = 0;
+        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+            const long long row = (long long)mt * BM + q * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            int cur_seg = 0, r = 0;                  // current segment and index inside its stride
+            float best = -INFINITY;
+            int best_idx = 0;
+            for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
+                const int acc = tcount & 1;
+                const uint32_t aph = (tcount >> 1) & 1;
+                mbar_wait(bar_tfull(acc), aph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        if (r < p.seg_len && cur_seg < p.n_seg && x > best) { best = x; best_idx = r; }
+                        if (++r == p.seg_stride) {
+                            if (row_ok && cur_seg < p.n_seg) {
+                                p.out_val[row * p.n_seg + cur_seg] = best;
+                                p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                            }
+                            r = 0; ++cur_seg; best = -INFINITY; best_idx = 0;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty(acc));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { olfnav_set_error("umma: cuTensorMapEncodeTiled not available"); return OLFNAV_ERR_CUDA; }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { olfnav_set_error("umma: cuTensorMapEncodeTiled failed (%d)", (int)r); return OLFNAV_ERR_CUDA; }
+    return OLFNAV_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl, const GemmParams& p, int grid, cudaStream_t st) {
+    using L = SmemLayout<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        OLF_CUDA(cudaFuncSetAttribute(umma_segmax_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    umma_segmax_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+}  // namespace
+
+int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
+                    int rows_b, int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count,
+                    cudaStream_t st) {
+    OLF_REQUIRE(A && B_hi && B_lo && out_val && out_arg, "umma_segmax: null argument");
+    OLF_REQUIRE((lda % 4) == 0 && (((uintptr_t)A) & 15) == 0, "umma_segmax: A must be 16-byte aligned with lda %% 4 == 0");
+    OLF_REQUIRE((ldb % 32) == 0 && ldb >= K, "umma_segmax: ldb must be a multiple of 32 and >= K");
+    OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax: bad segment layout");
+    OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax: empty problem");
+
+    const int BN = rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : (rows_b <= 128 ? 128 : 256));
+    GemmParams p;
+    p.n_rows = (int)n_rows; p.K = K; p.rows_b = rows_b;
+    p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
+    p.out_val = out_val; p.out_arg = out_arg;
+    p.num_m_tiles = olf_div_up(n_rows, BM);
+    p.num_n_tiles = olf_div_up(rows_b, BN);
+    p.num_k_blocks = olf_div_up(K, BK);
+
+    CUtensorMap tA, tBh, tBl;
+    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM);
+    if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b, (uint64_t)ldb * 4, BN);
+    if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b, (uint64_t)ldb * 4, BN);
+    if (rc != OLFNAV_OK) return rc;
+
+    const int grid = p.num_m_tiles < sm_count ? p.num_m_tiles : sm_count;
+    switch (BN) {
+        case 32:  return launch<32, 5>(tA, tBh, tBl, p, grid, st);
+        case 64:  return launch<64, 4>(tA, tBh, tBl, p, grid, st);
+        case 128: return launch<128, 3>(tA, tBh, tBl, p, grid, st);
+        default:  return launch<256, 2>(tA, tBh, tBl, p, grid, st);
+    }
+}

@@ -1,0 +1,15 @@
+// tcgen05 split-precision GEMM with fused segmented max/argmax epilogue (see umma_gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// out_val[i][s] = max_{g < seg_len} A[i,:] . B[s*seg_stride + g,:]   (3xTF32, FP32 accumulate)
+// out_arg[i][s] = first argmax g.
+//   A      [n_rows x K] fp32, row stride lda (multiple of 4 floats, 16-byte aligned base)
+//   B_hi/B_lo [rows_b x ldb] fp32 planes whose values are exactly TF32-representable
+//             (low 13 mantissa bits zero), ldb a multiple of 32, >= K, zero beyond K.
+//   rows_b = n_seg * seg_stride, seg_stride a multiple of 16.
+int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K,
+                    const float* B_hi, const float* B_lo, int64_t ldb, int rows_b,
+                    int n_seg, int seg_len, int seg_stride,
+                    float* out_val, int* out_arg, int sm_count, cudaStream_t st);

@@ -1,0 +1,401 @@
+'''
+Device solvers — the `pomdp_toolkit.solvers` surface the reference's agents call:
+  VI.solve                 reference agents/qmdp_agent.py:145-153 (and implicitly FSVI, agents/fsvi_agent.py:154-158)
+  FSVI.solve               reference agents/fsvi_agent.py:201-224
+  PBVI_RA/SSRA/SSGA/SSEA   reference agents/pbvi_ra_agent.py:168, pbvi_ssra_agent.py:170,
+                           pbvi_ssga_agent.py:176-198, pbvi_ssea_agent.py:170
+  PBVI_GER/Perseus/HSVI    expand heuristics are SURVEY §8 f2 ("next"): NotImplementedError.
+
+The backup runs on the device in three steps through the C ABI:
+  olfnav_backup_gamma    Gamma_{a,o}^g = gamma * O_o(R_a(.)) * alpha_g(R_a(.))          streaming kernel
+  olfnav_backup_select   g*(b,a,o) = argmax_g b.Gamma_{a,o}^g ; a*(b)                    tcgen05 GEMM + segmented argmax
+  olfnav_backup_assemble alpha^b = r_{a*} + sum_o Gamma_{a*,o}^{g*}                      streaming kernel
+Host code keeps only the control flow, the (belief-free) trajectory sampling and the
+duplicate-vector pruning.  Random draws follow the same documented order as the oracle so that
+identical generators give identical (action, observation) sequences.
+'''
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from ._lib import lib, ptr, stream, check
+from .pomdp import POMDP, Belief, BeliefSet, ValueFunction, current_device
+
+
+class SolverHistory:
+    'Statistics of a solve(); fields follow the reference\'s TrainingHistory (agents/pbvi_agent.py:139-234).'
+    def __init__(self, model: POMDP, tracking_level: int, gamma: float, eps: float, solver: str) -> None:
+        self.model, self.tracking_level, self.gamma, self.eps, self.solver = model, tracking_level, gamma, eps, solver
+        self.expansion_times, self.backup_times, self.pruning_times = [], [], []
+        self.alpha_vector_counts, self.beliefs_counts, self.prune_counts = [], [], []
+        self.value_function_changes, self.iteration_times = [], []
+        self.value_functions, self.belief_sets = [], []
+        self.total_time = 0.0
+
+    @property
+    def summary(self) -> str:
+        m = self.model
+        if self.solver == 'VI':
+            n, tot = len(self.value_function_changes), self.total_time
+            return (f'Summary of Value Iteration run\n  - Model: {m.state_count}-state, {m.action_count}-action\n'
+                    f'  - Converged in {n} iterations and {tot:.4f} seconds\n'
+                    f'  - Took on average {(tot / max(n, 1)):.4f}s per iteration\n')
+        ne, nb = len(self.expansion_times), len(self.backup_times)
+        s = (f'Summary of Point Based Value Iteration run\n'
+             f'  - Model: {m.state_count} state, {m.action_count} action, {m.observation_count} observations\n'
+             f'  - Converged or stopped after {ne} expansion steps and {nb} backup steps.\n'
+             f'  - Resulting value function has {self.alpha_vector_counts[-1] if self.alpha_vector_counts else 0} alpha vectors.\n'
+             f'  - Converged in {self.total_time:.4f}s\n\n')
+        if ne:
+            s += (f'  - Expand function took on average {np.mean(self.expansion_times):.4f}s and yielded on average '
+                  f'{np.mean(self.beliefs_counts):.2f} beliefs per iteration.\n')
+        if nb:
+            s += (f'  - Backup function took on average {np.mean(self.backup_times):.4f}s and yielded on average '
+                  f'{np.mean(np.diff([0] + self.alpha_vector_counts)):.2f} alpha vectors per iteration.\n')
+        if self.pruning_times:
+            s += (f'  - Pruning function took on average {np.mean(self.pruning_times):.4f}s and yielded on average prunings of '
+                  f'{np.mean(self.prune_counts):.2f} alpha vectors per iteration.\n')
+        return s
+
+
+# =================================================================================================
+class VI:
+    @staticmethod
+    def solve(model: POMDP, horizon: int = 1000, initial_value_function: ValueFunction = None, gamma: float = 0.99,
+              eps: float = 1e-6, use_gpu: bool = True, use_reachability: bool = True, history_tracking_level: int = 1,
+              print_progress: bool = True, check_every: int = 16):
+        '''
+        Q_a(s) = r_a(s) + gamma * max_a' Q_a'(R_a(s)); stops after the first sweep whose
+        max |V_k - V_{k-1}| < eps / (1 - gamma) (918 sweeps at gamma=.99, eps=1e-6, the count the
+        reference's notebooks print).  float64 sweeps on the device; the per-sweep change is read
+        back every `check_every` sweeps and the stop sweep is then replayed exactly.
+        '''
+        device = current_device()
+        dev = torch.device('cuda', device)
+        hist = SolverHistory(model, history_tracking_level, gamma, eps, 'VI')
+        t0 = time.perf_counter()
+        Sp, A = model.padded_states, model.action_count
+        h = model.handle(device)
+        Q = torch.zeros((2, A, Sp), dtype=torch.float64, device=dev)
+        if initial_value_function is not None:
+            Q[0] = initial_value_function.device_alphas(device).double()
+        threshold = eps / (1.0 - gamma)
+        changes = torch.zeros(max(horizon, 1), dtype=torch.float64, device=dev)
+        done, cur = 0, 0
+        while done < horizon:
+            block = min(check_every, horizon - done)
+            snapshot = Q[cur].clone()
+            for k in range(block):
+                check(lib.olfnav_vi_sweep(h, ptr(Q[cur]), ptr(Q[1 - cur]), Sp, gamma, ptr(changes[done + k:]), stream()))
+                cur = 1 - cur
+            ch = changes[done:done + block].cpu().numpy()
+            below = np.flatnonzero(ch < threshold)
+            if len(below):
+                # replay from the snapshot up to (and including) the first sweep below the threshold
+                stop = int(below[0]) + 1
+                Q[0] = snapshot
+                cur = 0
+                changes[done:done + block] = 0
+                for k in range(stop):
+                    check(lib.olfnav_vi_sweep(h, ptr(Q[cur]), ptr(Q[1 - cur]), Sp, gamma, ptr(changes[done + k:]), stream()))
+                    cur = 1 - cur
+                done += stop
+                break
+            done += block
+        hist.value_function_changes = changes[:done].cpu().numpy().tolist()
+        alphas = Q[cur].float().contiguous()
+        vf = ValueFunction(model, action_list=model.actions, _device_alphas=alphas)
+        torch.cuda.synchronize(dev)
+        hist.total_time = time.perf_counter() - t0
+        hist.iteration_times = [hist.total_time / max(done, 1)] * done
+        hist.alpha_vector_counts.append(len(vf))
+        return vf, hist
+
+
+# =================================================================================================
+def backup_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tensor, gamma: float, path: int = 0):
+    '''
+    One point-based backup of the alpha set `alphas` (G, Sp) at every belief of the set.
+    Returns device tensors: new_alpha (B, Sp) f32, best_a (B,) i32, new_value (B,) f32 (value of the
+    new vector at its belief), best_g (B, A, O) i32.
+    '''
+    device = belief_set.device
+    dev = torch.device('cuda', device)
+    h = model.handle(device)
+    A, O, Sp = model.action_count, model.observation_count, model.padded_states
+    G, B = alphas.shape[0], len(belief_set)
+    gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=dev)
+    best_g = torch.empty((B, A, O), dtype=torch.int32, device=dev)
+    best_a = torch.empty(B, dtype=torch.int32, device=dev)
+    best_v = torch.empty(B, dtype=torch.float32, device=dev)
+    new_alpha = torch.empty((B, Sp), dtype=torch.float32, device=dev)
+    with torch.cuda.device(device):
+        check(lib.olfnav_backup_gamma(h, ptr(alphas), alphas.stride(0), G, gamma, ptr(gam), Sp, stream()))
+        check(lib.olfnav_backup_select(h, ptr(belief_set._b), belief_set.ld, B, ptr(belief_set._scale), ptr(gam), Sp, G,
+                                       ptr(best_g), ptr(best_a), ptr(best_v), path, stream()))
+        check(lib.olfnav_backup_assemble(h, ptr(gam), Sp, G, ptr(best_g), ptr(best_a), B, ptr(new_alpha), Sp, stream()))
+    return new_alpha, best_a, best_v, best_g
+
+
+def _unique_rows(alpha: torch.Tensor, actions: torch.Tensor):
+    'Drop exact duplicate (vector, action) rows, keep the first occurrence and the original order.'
+    if alpha.shape[0] <= 1:
+        return alpha, actions
+    keyed = torch.cat([actions.float()[:, None], alpha], dim=1)
+    _, inverse = torch.unique(keyed, dim=0, return_inverse=True)
+    first = torch.full((int(inverse.max()) + 1,), alpha.shape[0], dtype=torch.long, device=alpha.device)
+    first.scatter_reduce_(0, inverse, torch.arange(alpha.shape[0], device=alpha.device), reduce='amin')
+    keep = torch.sort(first).values
+    return alpha[keep], actions[keep]
+
+
+class _PBVI:
+    name = 'PBVI'
+    full_backup = True
+    dominance_prune = False
+
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, **kw) -> dict:
+        return {}
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, **kw) -> BeliefSet:
+        raise NotImplementedError
+
+    @classmethod
+    def solve(cls, model: POMDP, expansions: int = 10, update_passes: int = 1, max_belief_growth: int = 10,
+              initial_belief=None, initial_value_function: ValueFunction = None, prune_level: int = 1,
+              prune_interval: int = 10, limit_value_function_size: int = -1, gamma: float = 0.99, eps: float = 1e-6,
+              convergence_stop: bool = False, use_gpu: bool = True, use_reachability: bool = True,
+              rng: np.random.Generator = None, history_tracking_level: int = 1, print_progress: bool = True,
+              print_stats: bool = True, gemm_path: int = 0, **flavour):
+        rng = np.random.default_rng() if rng is None else rng
+        device = current_device()
+        dev = torch.device('cuda', device)
+        hist = SolverHistory(model, history_tracking_level, gamma, eps, cls.name)
+        t_start = time.perf_counter()
+        extra = cls.prepare(model, gamma, eps, print_progress, use_reachability=use_reachability, **flavour)
+
+        if initial_belief is None:
+            belief_set = BeliefSet(model, 1)
+        elif isinstance(initial_belief, Belief):
+            belief_set = BeliefSet(model, initial_belief.values[None, :])
+        else:
+            belief_set = initial_belief
+
+        if initial_value_function is None:
+            vf0 = ValueFunction(model, model.expected_rewards_table.T.copy(), model.actions)
+        else:
+            vf0 = initial_value_function
+        alphas = vf0.device_alphas(device).clone()
+        actions = torch.as_tensor(vf0.actions, dtype=torch.int32, device=dev)
+
+        def values_of(bs, al, ac):
+            v, _, _ = ValueFunction(model, action_list=ac.cpu().numpy(), _device_alphas=al).evaluate_device(bs, gemm_path)
+            return v
+
+        old_values = values_of(belief_set, alphas, actions)
+        backup_count = 0
+        for _ in range(expansions):
+            t0 = time.perf_counter()
+            new_beliefs = cls.expand(model, belief_set, alphas, actions, max_belief_growth, rng, **extra)
+            belief_set = belief_set.union(new_beliefs)
+            torch.cuda.synchronize(dev)
+            hist.expansion_times.append(time.perf_counter() - t0)
+            hist.beliefs_counts.append(len(belief_set))
+
+            t0 = time.perf_counter()
+            target = belief_set if cls.full_backup else new_beliefs
+            for _ in range(update_passes):
+                if len(target) == 0:
+                    break
+                new_alpha, best_a, new_v, _ = backup_device(model, target, alphas, gamma, gemm_path)
+                if cls.dominance_prune:
+                    keep = new_v > values_of(target, alphas, actions)
+                    new_alpha, best_a = new_alpha[keep], best_a[keep]
+                new_alpha, best_a = _unique_rows(new_alpha, best_a)
+                if cls.full_backup:
+                    alphas, actions = new_alpha, best_a
+                else:
+                    alphas, actions = _unique_rows(torch.cat([alphas, new_alpha]), torch.cat([actions, best_a]))
+                backup_count += 1
+            torch.cuda.synchronize(dev)
+            hist.backup_times.append(time.perf_counter() - t0)
+
+            t0 = time.perf_counter()
+            pruned = 0
+            if prune_interval > 0 and (backup_count % prune_interval) == 0 and prune_level >= 1:
+                before = alphas.shape[0]
+                alphas, actions = _unique_rows(alphas, actions)
+                pruned = before - alphas.shape[0]
+            if 0 < limit_value_function_size < alphas.shape[0]:
+                G = alphas.shape[0]
+                drop = rng.choice(G, size=min(max_belief_growth, G - 1), replace=False)
+                keep = np.ones(G, dtype=bool)
+                keep[drop] = False
+                keep_t = torch.as_tensor(keep, device=dev)
+                alphas, actions = alphas[keep_t], actions[keep_t]
+                pruned += int((~keep).sum())
+            hist.pruning_times.append(time.perf_counter() - t0)
+            hist.prune_counts.append(pruned)
+            hist.alpha_vector_counts.append(int(alphas.shape[0]))
+
+            new_values = values_of(belief_set, alphas, actions)
+            change = float((new_values[:len(old_values)] - old_values).abs().max()) if len(old_values) else float('inf')
+            old_values = new_values
+            hist.value_function_changes.append(change)
+            if convergence_stop and change < eps:
+                break
+
+        value_function = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas.contiguous())
+        hist.total_time = time.perf_counter() - t_start
+        hist.final_belief_set = belief_set
+        if 'mdp_policy' in extra and flavour.get('return_mdp_policy', False):
+            return value_function, hist, extra['mdp_policy']
+        return value_function, hist
+
+
+def _chain_updates(model: POMDP, b0: BeliefSet, row: int, seq) -> BeliefSet:
+    'Beliefs visited by applying the (action, observation) sequence to row `row` of b0, one kernel launch per step.'
+    device = b0.device
+    dev = b0._b.device
+    n = len(seq)
+    Sp = model.padded_states
+    out_b = torch.empty((max(n, 1), Sp), dtype=torch.float32, device=dev)
+    out_s = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    ok = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    if n == 0:
+        return BeliefSet(model, _buffers=(out_b, out_s, 0), device=device)
+    acts = torch.as_tensor([a for a, _ in seq], dtype=torch.int32, device=dev)
+    obss = torch.as_tensor([o for _, o in seq], dtype=torch.int32, device=dev)
+    h = model.handle(device)
+    with torch.cuda.device(device):
+        for k in range(n):
+            src_b = b0._b[row:row + 1] if k == 0 else out_b[k - 1:k]
+            src_s = b0._scale[row:row + 1] if k == 0 else out_s[k - 1:k]
+            check(lib.olfnav_belief_step(h, ptr(src_b), ptr(out_b[k:k + 1]), Sp, 1, ptr(acts[k:k + 1]), ptr(obss[k:k + 1]),
+                                         None, None, ptr(src_s), ptr(out_s[k:k + 1]), ptr(ok[k:k + 1]), stream()))
+    if not bool(ok[:n].all()):
+        raise ValueError('Impossible belief update during expand')
+    return BeliefSet(model, _buffers=(out_b, out_s, n), device=device)
+
+
+class FSVI(_PBVI):
+    '''
+    Forward Search Value Iteration (Shani et al., cited at agents/fsvi_agent.py:12): one trajectory
+    per expansion from the initial belief under the MDP policy; the (action, observation) sequence
+    is belief-free so it is sampled on the host and the beliefs are produced by chained belief-step
+    launches.  Backup on the new beliefs only, appended (agents/fsvi_agent.py:139).
+    '''
+    name = 'FSVI'
+    full_backup = False
+    dominance_prune = True
+
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, mdp_policy=None, vi_horizon=1000, use_reachability=True, **kw):
+        if mdp_policy is None:
+            mdp_policy, _ = VI.solve(model, horizon=vi_horizon, gamma=gamma, eps=eps, print_progress=print_progress)
+        return {'mdp_policy': mdp_policy, 'Q': mdp_policy.alpha_vector_array}
+
+    @staticmethod
+    def trajectory(model: POMDP, b0: np.ndarray, Q: np.ndarray, max_generation: int, rng) -> list:
+        cdf = np.cumsum(b0)
+        s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
+        seq = []
+        for _ in range(max_generation):
+            a = int(np.argmax(Q[:, s]))
+            s_p = model.transition(s, a)
+            o = model.observe(s_p, a, rng.random())
+            seq.append((a, o))
+            s = s_p
+            if model.end_mask[s]:
+                break
+        return seq
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, mdp_policy=None, Q=None, **kw) -> BeliefSet:
+        b0 = belief_set.belief_tensor(torch.float64)[0].cpu().numpy() if len(belief_set) else model.start_probabilities
+        seq = cls.trajectory(model, b0, Q, max_generation, rng)
+        return _chain_updates(model, belief_set, 0, seq)
+
+
+class PBVI_SSRA(_PBVI):
+    'Stochastic Simulation with Random Action (same draw order as the oracle).'
+    name = 'PBVI_SSRA'
+
+    @classmethod
+    def choose_action(cls, model, k, belief_set, alphas, actions, rng, **kw) -> int:
+        return min(int(rng.random() * model.action_count), model.action_count - 1)
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, **kw) -> BeliefSet:
+        m = min(max_generation, len(belief_set))
+        dense = belief_set.belief_tensor(torch.float64)[:m].cpu().numpy()
+        pieces = None
+        for k in range(m):
+            cdf = np.cumsum(dense[k])
+            s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
+            a = cls.choose_action(model, k, belief_set, alphas, actions, rng, **kw)
+            s_p = model.transition(s, a)
+            o = model.observe(s_p, a, rng.random())
+            nb = _chain_updates(model, belief_set, k, [(a, o)])
+            pieces = nb if pieces is None else pieces.union(nb)
+        return pieces if pieces is not None else BeliefSet(model, np.zeros((0, model.state_count)))
+
+
+class PBVI_SSGA(PBVI_SSRA):
+    'Stochastic Simulation with Greedy Action, epsilon-greedy (agents/pbvi_ssga_agent.py:176-198).'
+    name = 'PBVI_SSGA'
+
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, epsilon=0.1, epsilon_decay=1.0, **kw):
+        return {'epsilon_state': {'epsilon': float(epsilon), 'decay': float(epsilon_decay)}}
+
+    @classmethod
+    def choose_action(cls, model, k, belief_set, alphas, actions, rng, epsilon_state=None, **kw) -> int:
+        if rng.random() < epsilon_state['epsilon']:
+            return min(int(rng.random() * model.action_count), model.action_count - 1)
+        one = BeliefSet(model, _buffers=(belief_set._b[k:k + 1], belief_set._scale[k:k + 1], 1), device=belief_set.device)
+        _, _, act = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas).evaluate_device(one)
+        return int(act[0])
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, epsilon_state=None, **kw) -> BeliefSet:
+        out = super().expand(model, belief_set, alphas, actions, max_generation, rng, epsilon_state=epsilon_state)
+        epsilon_state['epsilon'] *= epsilon_state['decay']
+        return out
+
+
+class PBVI_RA(_PBVI):
+    'Random belief selection: Dirichlet(1) points from rng.random((n, S)) (same draws as the oracle).'
+    name = 'PBVI_RA'
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, **kw) -> BeliefSet:
+        pts = -np.log(1.0 - rng.random((max_generation, model.state_count)))
+        return BeliefSet(model, pts / np.sum(pts, axis=1, keepdims=True))
+
+
+class _Next(_PBVI):
+    @classmethod
+    def solve(cls, *args, **kwargs):
+        raise NotImplementedError(f'{cls.name}: expand heuristic not built yet (SURVEY §8 f2, "next"); it shares the device backup.')
+
+
+class PBVI_SSEA(_Next):
+    name = 'PBVI_SSEA'
+
+
+class PBVI_GER(_Next):
+    name = 'PBVI_GER'
+
+
+class Perseus(_Next):
+    name = 'Perseus'
+
+
+class HSVI(_Next):
+    name = 'HSVI'
