@@ -8,12 +8,17 @@
 // low 13 mantissa bits cleared (exactly TF32) and x_lo = trunc_tf32(x - x_hi).  The dropped terms are
 // below 2^-21 |a||b|, which protects the argmax the same way an FP32 FMA chain does.
 //
+// Two-level accumulation: the tensor core adds into its FP32 accumulator with truncation (measured on B200:
+// a relative bias of about -1.5e-8 per accumulate, -2e-4 after the 11 580 accumulates of K = 30 876).  The
+// accumulator therefore only lives for KCHUNK k-blocks (48 MMAs); the epilogue warps then add the partial
+// sums into FP32 registers (round to nearest) while the MMA warp fills the other TMEM buffer.
+//
 // Warp roles (384 threads, one CTA per SM, persistent over 128-row tiles of A):
 //   warp 0      TMA producer: A tile (raw FP32) + B_hi + B_lo tiles, 128B swizzle, mbarrier complete_tx
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32, tcgen05.commit frees stages
 //   warp 2      TMEM allocator
 //   warps 4-7   A transform: split the raw tile in place into hi (same buffer) and lo (second buffer)
-//   warps 8-11  epilogue: tcgen05.ld the accumulator, running segmented max/argmax in registers
+//   warps 8-11  epilogue: tcgen05.ld each K-chunk's partial accumulator, FP32 register sums, segmented max/argmax
 // Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
 #include "common.cuh"
 #include "umma_gemm.cuh"
@@ -26,6 +31,7 @@ constexpr int BM = 128;          // rows of A per tile (UMMA M)
 constexpr int BK = 32;           // K per block: 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;        // K per tcgen05.mma.kind::tf32
 constexpr int NTHREADS = 384;
+constexpr int KCHUNK = 4;        // k-blocks accumulated inside TMEM before the partial sum is flushed to registers
 constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
 
 struct GemmParams {
@@ -87,6 +93,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -177,33 +192,36 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32<BN>();
-        uint32_t it = 0, tcount = 0;
+        uint32_t it = 0, ccount = 0;
         for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
-            for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
-                const int acc = tcount & 1;
-                const uint32_t aph = (tcount >> 1) & 1;
-                mbar_wait(bar_tempty(acc), aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_ready(s), ph);
+            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+                for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                    const int acc = ccount & 1;
+                    const uint32_t aph = (ccount >> 1) & 1;
+                    mbar_wait(bar_tempty(acc), aph ^ 1);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
-                        const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const int kb1 = min(KB, kb0 + KCHUNK);
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(bar_ready(s), ph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
+                            const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
-                            tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-                            tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
-                            tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
+                                tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                                tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+                                tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+                            }
+                            tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
+                            if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
                         }
-                        tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
-                        if (kb == KB - 1) tc_commit(bar_tfull(acc));
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -241,39 +259,56 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else if (warp >= 8) {
-        // ===================== epilogue: segmented running max / argmax =====================
+        // ===================== epilogue: FP32 register accumulation + segmented max / argmax =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        uint32_t tcount = 0;
+        uint32_t ccount = 0;
         for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
             const long long row = (long long)mt * BM + q * 32 + lane;
             const bool row_ok = row < p.n_rows;
             int cur_seg = 0, r = 0;                  // current segment and index inside its stride
             float best = -INFINITY;
             int best_idx = 0;
-            for (int nt = 0; nt < p.num_n_tiles; ++nt, ++tcount) {
-                const int acc = tcount & 1;
-                const uint32_t aph = (tcount >> 1) & 1;
-                mbar_wait(bar_tfull(acc), aph);
-                tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
+                float sum[BN];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        if (r < p.seg_len && cur_seg < p.n_seg && x > best) { best = x; best_idx = r; }
-                        if (++r == p.seg_stride) {
-                            if (row_ok && cur_seg < p.n_seg) {
-                                p.out_val[row * p.n_seg + cur_seg] = best;
-                                p.out_arg[row * p.n_seg + cur_seg] = best_idx;
-                            }
-                            r = 0; ++cur_seg; best = -INFINITY; best_idx = 0;
+                for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+                for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                    const int acc = ccount & 1;
+                    const uint32_t aph = (ccount >> 1) & 1;
+                    mbar_wait(bar_tfull(acc), aph);
+                    tc_fence_after();
+                    if constexpr (BN >= 128) {       // narrower loads: 128 running sums already fill the register file
+#pragma unroll
+                        for (int c0 = 0; c0 < BN; c0 += 16) {
+                            uint32_t v[16];
+                            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c0 = 0; c0 < BN; c0 += 32) {
+                            uint32_t v[32];
+                            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
                         }
                     }
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty(acc));
                 }
-                tc_fence_before();
-                mbar_arrive(bar_tempty(acc));
+#pragma unroll
+                for (int j = 0; j < BN; ++j) {
+                    const float x = sum[j];
+                    if (r < p.seg_len && cur_seg < p.n_seg && x > best) { best = x; best_idx = r; }
+                    if (++r == p.seg_stride) {
+                        if (row_ok && cur_seg < p.n_seg) {
+                            p.out_val[row * p.n_seg + cur_seg] = best;
+                            p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                        }
+                        r = 0; ++cur_seg; best = -INFINITY; best_idx = 0;
+                    }
+                }
             }
         }
     }
@@ -340,7 +375,7 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax: bad segment layout");
     OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax: empty problem");
 
-    const int BN = rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : (rows_b <= 128 ? 128 : 256));
+    const int BN = rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : 128);   // <= 128: the epilogue keeps BN FP32 partial sums in registers
     GemmParams p;
     p.n_rows = (int)n_rows; p.K = K; p.rows_b = rows_b;
     p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
@@ -359,7 +394,6 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     switch (BN) {
         case 32:  return launch<32, 5>(tA, tBh, tBl, p, grid, st);
         case 64:  return launch<64, 4>(tA, tBh, tBl, p, grid, st);
-        case 128: return launch<128, 3>(tA, tBh, tBl, p, grid, st);
-        default:  return launch<256, 2>(tA, tBh, tBl, p, grid, st);
+        default:  return launch<128, 3>(tA, tBh, tBl, p, grid, st);
     }
 }

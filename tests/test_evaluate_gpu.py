@@ -1,0 +1,144 @@
+'''
+Value-function evaluation (olfnav_evaluate) — FP32 SIMT path and tcgen05 3xTF32 path — and the
+PBVI backup (gamma build / select / assemble) against golden vectors and the oracle.
+Values within 1e-5 relative; argmax / action indices exact wherever the float64 margin between the two
+best candidates exceeds 1e-5 relative (documented ties below that).
+'''
+import numpy as np
+import pytest
+import torch
+
+from conftest import ALL_CFGS, golden, make, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('path', [1, 2])
+def test_evaluate_golden(cfg, path):
+    import olfactory_navigation_b200 as onb
+    g = golden(f'evaluate_{cfg}')
+    _, agent = make(cfg)
+    m = agent.model
+    vf = onb.ValueFunction(m, g['alphas'].astype(np.float64), g['alpha_actions'])
+    val, arg, act = vf.evaluate_device(onb.BeliefSet(m, g['beliefs'].astype(np.float64)), path)
+    np.testing.assert_allclose(val.cpu().numpy(), g['values'], rtol=1e-5)
+    clear = g['margin'] > 1e-5 * np.abs(g['values'])
+    assert clear.sum() >= 0.8 * len(clear)
+    assert np.array_equal(arg.cpu().numpy()[clear], g['argmax'][clear])
+    assert np.array_equal(act.cpu().numpy()[clear], g['actions'][clear])
+
+
+@pytest.mark.parametrize('G', [1, 4, 16, 17, 40, 130, 300])
+def test_evaluate_paths_agree_many_sizes(G):
+    'Row counts that do not fill a 128-row tile, G across every tile width (32/64/128/256 and 2 N-tiles).'
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(G)
+    n = 333
+    d = -np.log(1.0 - rng.random((n, m.state_count)))
+    B = (d / d.sum(1, keepdims=True)).astype(np.float32).astype(np.float64)
+    alphas = rng.standard_normal((G, m.state_count)).astype(np.float32).astype(np.float64)
+    acts = rng.integers(0, 4, G)
+    vf = onb.ValueFunction(m, alphas, acts)
+    bs = onb.BeliefSet(m, B)
+    sc = B @ alphas.T
+    ref_v, ref_g = sc.max(1), sc.argmax(1)
+    srt = np.sort(sc, axis=1)
+    clear = (srt[:, -1] - srt[:, -2] > 1e-5 * np.abs(srt).max()) if G > 1 else np.ones(n, bool)
+    for path in (1, 2):
+        val, arg, act = vf.evaluate_device(bs, path)
+        np.testing.assert_allclose(val.cpu().numpy(), ref_v, rtol=0, atol=1e-5 * np.abs(sc).max())   # signed random alphas: error scales with sum|a||b|
+        assert np.array_equal(arg.cpu().numpy()[clear], ref_g[clear])
+        assert np.array_equal(act.cpu().numpy()[clear], acts[ref_g][clear])
+
+
+def test_first_maximum_wins_on_exact_ties():
+    'Duplicate alpha vectors (backups emit them routinely): the lowest index must win on both paths.'
+    import olfactory_navigation_b200 as onb
+    _, agent = make('T1')
+    m = agent.model
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((3, m.state_count)).astype(np.float32).astype(np.float64)
+    alphas = np.vstack([base, base, base[::-1]])
+    vf = onb.ValueFunction(m, alphas, np.arange(9) % 4)
+    B = np.abs(rng.standard_normal((50, m.state_count)))
+    B /= B.sum(1, keepdims=True)
+    ref = (B.astype(np.float32).astype(np.float64) @ base.T).argmax(1)          # index among the three distinct vectors
+    for path in (1, 2):
+        _, arg, _ = vf.evaluate_device(onb.BeliefSet(m, B), path)
+        assert np.array_equal(arg.cpu().numpy(), ref)
+
+
+def test_evaluate_full_size_tensor_vs_simt():
+    'BASELINE shape, 4096 agents, G=64: tcgen05 path == FP32 SIMT path (values 1e-5, argmax where clear).'
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C2')
+    m = agent.model
+    rng = np.random.default_rng(1)
+    bs = onb.BeliefSet(m, 4096)
+    act = rng.integers(0, 4, 4096)
+    for _ in range(3):
+        bs = bs.update(act, np.zeros(4096, dtype=int))
+    alphas = np.abs(rng.standard_normal((64, m.state_count))).astype(np.float32).astype(np.float64)
+    vf = onb.ValueFunction(m, alphas, np.arange(64) % 4)
+    v1, g1, _ = vf.evaluate_device(bs, 1)
+    v2, g2, _ = vf.evaluate_device(bs, 2)
+    np.testing.assert_allclose(v2.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5)
+    assert float((g1 == g2).float().mean()) > 0.999
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('path', [1, 2])
+def test_backup_golden(cfg, path):
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+    g = golden(f'backup_{cfg}')
+    _, agent = make(cfg)
+    m = agent.model
+    bs = onb.BeliefSet(m, g['beliefs'].astype(np.float64))
+    vf = onb.ValueFunction(m, g['alphas'].astype(np.float64), np.zeros(len(g['alphas']), dtype=int))
+    alphas = vf.device_alphas(0)
+    if g['gamma_ao'].size:
+        # Gamma_{a,o} itself
+        A, O, G, Sp = m.action_count, m.observation_count, alphas.shape[0], m.padded_states
+        gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=alphas.device)
+        check(lib.olfnav_backup_gamma(m.handle(0), ptr(alphas), alphas.stride(0), G, float(g['discount']), ptr(gam), Sp, stream()))
+        dense = torch.empty((A * O * G, m.state_count), dtype=torch.float32, device=alphas.device)
+        check(lib.olfnav_unpack_rows(m.handle(0), ptr(gam), Sp, A * O * G, None, None, ptr(dense), stream()))
+        np.testing.assert_allclose(dense.cpu().numpy().reshape(A, O, G, -1), g['gamma_ao'], rtol=2e-6, atol=0)
+    new_alpha, best_a, best_v, best_g = onb.solvers.backup_device(m, bs, alphas, float(g['discount']), path)
+    best_a, best_g = best_a.cpu().numpy(), best_g.cpu().numpy()
+    scale = np.abs(g['new_value'])[:, None, None] + 1e-30
+    g_clear = g['g_margin'] > 1e-5 * scale
+    assert g_clear.mean() > 0.3
+    assert np.array_equal(best_g[g_clear], g['best_g'][g_clear])
+    a_clear = g['a_margin'] > 1e-5 * np.abs(g['new_value'])
+    assert a_clear.mean() > 0.5
+    assert np.array_equal(best_a[a_clear], g['best_a'][a_clear])
+    np.testing.assert_allclose(best_v.cpu().numpy(), g['new_value'], rtol=1e-5)
+    # assembly: alpha^b = r_{a*} + sum_o Gamma_{a*,o}^{g*}, checked with the DEVICE's own choices so ties do not matter
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    om = oracle_model(m)
+    gam = tk.solvers.gamma_a_o(om, g['alphas'].astype(np.float64), float(g['discount']))      # (A, O, G, S)
+    nb = len(best_a)
+    ref = om.expected_rewards_table.T[best_a] + sum(gam[best_a, o, best_g[np.arange(nb), best_a, o], :] for o in range(m.observation_count))
+    dense = onb.ValueFunction(m, action_list=np.zeros(nb, int), _device_alphas=new_alpha).alpha_vector_array
+    np.testing.assert_allclose(dense, ref, rtol=1e-5, atol=1e-7)
+    # and where nothing was tied the vectors are the oracle's
+    rows = a_clear & np.array([g_clear[b, g['best_a'][b]].all() for b in range(nb)])
+    np.testing.assert_allclose(dense[rows], g['new_alpha'][rows], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+def test_vi_918_sweeps(cfg):
+    import olfactory_navigation_b200 as onb
+    g = golden(f'vi_{cfg}')
+    _, agent = make(cfg)
+    vf, hist = onb.solvers.VI.solve(agent.model, horizon=1000, gamma=0.99, eps=1e-6)
+    assert len(hist.value_function_changes) == 918
+    np.testing.assert_allclose(hist.value_function_changes, g['changes'], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(vf.alpha_vector_array, g['Q'], rtol=1e-6)

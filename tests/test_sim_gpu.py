@@ -1,0 +1,211 @@
+'''
+Environment stepping, infotaxis choice, agents and run_test on the device against the golden vectors
+frozen from the UNMODIFIED reference's run_test / agents / Infotaxis loop (oracle/make_golden.py).
+'''
+import numpy as np
+import pytest
+import torch
+
+from conftest import ALL_CFGS, TINY, golden, make
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('quirk', [True, False])
+def test_env_step_bit_exact(cfg, quirk):
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+    g = golden(f'envstep_{cfg}')
+    env, agent = make(cfg)
+    dev = torch.device('cuda', 0)
+    n = len(g['act'])
+    pos = torch.as_tensor(g['pos'], dtype=torch.int32, device=dev).contiguous()
+    act = torch.as_tensor(g['act'], dtype=torch.int32, device=dev)
+    moves = torch.as_tensor(agent.action_set, dtype=torch.int32, device=dev).contiguous()
+    step = int(g['step'])
+    ts = g['time_shift']
+    if quirk:       # reference semantics: sorted effective times (Environment.reference_time_quirk)
+        t_eff, t_step = np.sort((ts + step) % env.timesteps), 0
+        want_odor, want_id = g['odor'], g['obs_id']
+    else:
+        t_eff, t_step = ts, step
+        env.reference_time_quirk = False
+        try:
+            want_odor = env.get_observation(g['new_pos'].astype(int), time=ts + step)
+        finally:
+            env.reference_time_quirk = True
+        want_id = agent.discretize_observations(want_odor, None, g['reached'])
+    tsh = torch.as_tensor(t_eff, dtype=torch.int64, device=dev)
+    thr = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev)
+    odor = torch.empty(n, dtype=torch.float64, device=dev)
+    oid = torch.empty(n, dtype=torch.int32, device=dev)
+    reached = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(lib.olfnav_env_step(env.device_handle(0), n, ptr(pos), ptr(act), ptr(moves), ptr(tsh), t_step, ptr(thr), len(agent.thresholds),
+                              ptr(odor), ptr(oid), ptr(reached), stream()))
+    assert np.array_equal(pos.cpu().numpy(), g['new_pos'])
+    assert np.array_equal(odor.cpu().numpy(), want_odor)
+    assert np.array_equal(reached.cpu().numpy().astype(bool), g['reached'])
+    assert np.array_equal(oid.cpu().numpy(), want_id)
+
+
+@pytest.mark.parametrize('cfg', TINY)
+def test_infotaxis_vs_reference_loop(cfg):
+    import olfactory_navigation_b200 as onb
+    g = golden(f'infotaxis_{cfg}')
+    env, _ = make(cfg)
+    c = onb.synthetic.config(cfg)
+    it = onb.agents.Infotaxis_Agent(env, thresholds=c['thresholds'])
+    B = g['beliefs'].astype(np.float64)
+    it.initialize_state(len(B), onb.BeliefSet(it.model, B))
+    ids = it.choose_action_device(return_delta_H=True).cpu().numpy()
+    np.testing.assert_allclose(it.last_delta_H.cpu().numpy(), g['delta_H'], rtol=2e-4, atol=2e-4)
+    clear = g['margin'] > 1e-3
+    assert np.array_equal(ids[clear], g['chosen'][clear])
+    H = onb.BeliefSet(it.model, B).entropies
+    np.testing.assert_allclose(H, g['entropies'], rtol=1e-4, atol=1e-5)
+    # reference protocol: movement vectors
+    it.initialize_state(len(B), onb.BeliefSet(it.model, B))
+    mv = it.choose_action()
+    assert np.array_equal(mv[clear], g['moves'][clear])
+
+
+def _compare_runs(hist, g, min_same=0.85):
+    ref_done, ref_reached = g['done_at_step'], g['reached_source']
+    n = len(ref_done)
+    acts, poss = np.array(hist.actions), np.array(hist.positions)
+    r_acts, r_poss = g['actions'].astype(int), g['positions'].astype(int)
+    same = np.zeros(n, dtype=bool)
+    for k in range(n):
+        if hist.done_at_step[k] != ref_done[k] or hist.reached_source[k] != ref_reached[k]:
+            continue
+        steps = len(r_acts) if ref_done[k] < 0 else ref_done[k]
+        if len(acts) < steps:
+            continue
+        same[k] = np.array_equal(acts[:steps, k], r_acts[:steps, k]) and np.array_equal(poss[:steps, k], r_poss[:steps, k])
+    # float32 near-ties can flip an argmax and send a trajectory elsewhere; identical trajectories must dominate
+    assert same.mean() >= min_same, f'only {same.mean():.2%} of trajectories identical to the reference run'
+    return same
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('label', ['qmdp', 'fsvi'])
+def test_run_test_matches_reference_run(cfg, label):
+    'Same start points / time shifts / value function as the reference run -> same trajectories.'
+    import olfactory_navigation_b200 as onb
+    g = golden(f'runtest_{label}_{cfg}')
+    env, _ = make(cfg)
+    c = onb.synthetic.config(cfg)
+    agent = onb.agents.PBVI_Agent(env, thresholds=c['thresholds'])
+    agent.value_function = onb.ValueFunction(agent.model, g['alphas'].astype(np.float64), g['alpha_actions'])
+    hist = onb.run_test(agent, n=len(g['start_points']), start_points=g['start_points'].astype(int), time_shift=g['time_shift'],
+                        horizon=int(g['horizon']), print_progress=False, print_stats=False, batches=1)
+    same = _compare_runs(hist, g)
+    # observations of identical trajectories are bit exact (float64 odor data on the device)
+    obs = np.array(hist.observations)
+    for k in np.flatnonzero(same)[:10]:
+        steps = len(g['actions']) if g['done_at_step'][k] < 0 else g['done_at_step'][k]
+        assert np.array_equal(obs[:steps, k].astype(np.float32), g['observations'][:steps, k])
+    # batching splits and re-concatenates like the reference (simulation.py:1370-1413)
+    hist_b = onb.run_test(agent, n=len(g['start_points']), start_points=g['start_points'].astype(int), time_shift=g['time_shift'],
+                          horizon=int(g['horizon']), print_progress=False, print_stats=False, batches=3)
+    assert hist_b.n == hist.n and len(hist_b.done_at_step) == hist.n
+
+
+def test_reference_protocol_loop_equals_device_loop():
+    'Driving the agent through the NumPy protocol exactly like the reference run_test (simulation.py:1452-1497).'
+    import olfactory_navigation_b200 as onb
+    g = golden('runtest_fsvi_T1')
+    env, _ = make('T1')
+    c = onb.synthetic.config('T1')
+    agent = onb.agents.PBVI_Agent(env, thresholds=c['thresholds'])
+    agent.value_function = onb.ValueFunction(agent.model, g['alphas'].astype(np.float64), g['alpha_actions'])
+    n, horizon = len(g['start_points']), int(g['horizon'])
+    pos, tshift = g['start_points'].astype(int), g['time_shift'].astype(int)
+    agent.initialize_state(n)
+    hist = onb.SimulationHistory(pos, env, agent, tshift, horizon)
+    for i in range(horizon):
+        action = agent.choose_action()
+        pos = env.move(pos, action)
+        observation = env.get_observation(pos, time=tshift + i)
+        reached = env.source_reached(pos)
+        ok = agent.update_state(action=action, observation=observation, source_reached=reached)
+        term = reached | ~ok
+        hist.add_step(actions=action, next_positions=pos, observations=observation, reached_source=reached, interupt=term)
+        pos, tshift = pos[~term], tshift[~term]
+        agent.kill(simulations_to_kill=term)
+        if len(pos) == 0:
+            break
+    _compare_runs(hist, g)
+
+
+def test_failed_updates_and_extra_kills():
+    'Impossible observation -> ok False, agent terminated; kill() with extra victims compacts the rest.'
+    import olfactory_navigation_b200 as onb
+    env, _ = make('T0')
+    c = onb.synthetic.config('T0')
+    agent = onb.agents.QMDP_Agent(env, thresholds=c['thresholds'])
+    agent.train(print_progress=False, print_stats=False)
+    n = 6
+    agent.initialize_state(n)
+    agent.choose_action()
+    reached = np.array([False, True, False, False, False, False])
+    ok = agent.update_state(action=None, observation=np.zeros(n), source_reached=reached)
+    assert ok.all()
+    agent.kill(np.array([False, True, False, True, False, False]))           # extra kill of agent 3
+    assert len(agent.belief) == 4
+    np.testing.assert_allclose(agent.belief.belief_array.sum(1), 1.0, rtol=1e-5)
+    # 'something' can never be observed in the margins: point masses in a margin corner make the update impossible
+    m = agent.model
+    corner = np.zeros((4, m.state_count))
+    corner[:, 0] = 1.0
+    corner[3] = m.start_probabilities
+    agent.initialize_state(4, onb.BeliefSet(m, corner))
+    agent.choose_action()
+    okd = agent.update_state_device(torch.ones(4, dtype=torch.int32, device='cuda'), torch.zeros(4, dtype=torch.bool, device='cuda'))
+    assert okd.cpu().tolist() == [False, False, False, True]
+    agent.kill_device(~okd)
+    assert len(agent.belief) == 1
+    agent.choose_action()
+    okd = agent.update_state_device(torch.zeros(1, dtype=torch.int32, device='cuda'), torch.ones(1, dtype=torch.bool, device='cuda'))
+    agent.kill_device(torch.ones(1, dtype=torch.bool, device='cuda'))
+    assert agent.belief is None
+    with pytest.raises(RuntimeError):
+        agent.initialize_state(2)
+        agent.choose_action()
+        agent.update_state(None, np.zeros(2), np.array([True, False]))
+        agent.kill(np.array([False, False]))                                  # reached agent not killed
+
+
+def test_fsvi_training_on_device_and_save_load(tmp_path):
+    import olfactory_navigation_b200 as onb
+    env, _ = make('T1')
+    c = onb.synthetic.config('T1')
+    agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=7)
+    hist = agent.train(expansions=6, max_belief_growth=10, print_progress=False, print_stats=False)
+    assert agent.trained and len(agent.value_function) >= agent.model.action_count
+    assert len(hist.backup_times) == 6 and 'Point Based Value Iteration' in hist.summary
+    assert agent.mdp_policy is not None and len(agent.mdp_policy) == 4
+    h = onb.run_test(agent, n=64, horizon=80, print_progress=False, print_stats=False)
+    assert h.success_count > 0
+    agent.save(folder=str(tmp_path))
+    again = onb.agents.PBVI_Agent.load(agent.saved_at, environment=env)
+    assert isinstance(again, onb.agents.FSVI_Agent)
+    np.testing.assert_array_equal(again.value_function.alpha_vector_array, agent.value_function.alpha_vector_array)
+    assert np.array_equal(again.value_function.actions, agent.value_function.actions)
+
+
+def test_fsvi_matches_oracle_solver_alpha_count():
+    'Same RNG -> same (a, o) trajectories -> comparable value functions: every oracle alpha has a device twin.'
+    import olfactory_navigation_b200 as onb
+    from conftest import oracle_model
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    env, _ = make('T1')
+    c = onb.synthetic.config('T1')
+    agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'])
+    vf_d, _, _ = onb.solvers.FSVI.solve(agent.model, expansions=4, max_belief_growth=8, rng=np.random.default_rng(11), return_mdp_policy=True, print_progress=False)
+    vf_o, _, _ = tk.solvers.FSVI.solve(oracle_model(agent.model), expansions=4, max_belief_growth=8, rng=np.random.default_rng(11), return_mdp_policy=True, print_progress=False)
+    A_d, A_o = vf_d.alpha_vector_array, vf_o.alpha_vector_array
+    matched = sum(np.any(np.all(np.isclose(A_d, a[None, :], rtol=1e-4, atol=1e-6), axis=1)) for a in A_o)
+    assert matched >= 0.8 * len(A_o)
