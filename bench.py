@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+'''
+bench.py — agent belief-steps/s of the device-resident run_test step (BASELINE.json configs[1]):
+run_test of a trained FSVI agent on the 55x247 plume with 14/62 margins (83x371 = 30 793 states),
+100 000 parallel agents per GPU, synthetic seeded plume (olfactory_navigation_b200.synthetic 'C2').
+
+A "step" = one pass of the hot path over all live agents: choose_action (value-function evaluation)
+-> move / observe / source check / discretise -> fused belief update (+ compaction of finished agents).
+
+  value     device-resident loop (inputs already in HBM), agent-steps / s, all ranks
+  e2e       the same through the public API (`olfactory_navigation_b200.run_test`) with HOST inputs and
+            the per-step history records copied back to pinned host memory inside the timed region
+  roofline  fused belief-step kernel: 8 * S * live-agents algorithmic bytes per launch / CUDA-event time
+  cpu_baseline / --impl reference   the oracle's NumPy restatement of the reference loop (oracle/sim.py)
+            on the host cores (the reference is pure Python over the absent pomdp_toolkit and cannot travel)
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1 under torchrun, one rank per GPU).
+'''
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG = 'C2'
+N_AGENTS = 100_000
+TRAIN = dict(expansions=30, max_belief_growth=15)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--agents', type=int, default=N_AGENTS, help='agents per GPU (default: the BASELINE config)')
+    ap.add_argument('--cpu-agents', type=int, default=256)
+    ap.add_argument('--cpu-steps', type=int, default=12)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    'nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).'
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# =================================================================================================
+_CPU_SETUP = None
+
+
+def cpu_setup():
+    'Oracle-side model of the same workload (NumPy fp64), built once.'
+    global _CPU_SETUP
+    if _CPU_SETUP is not None:
+        return _CPU_SETUP
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    from oracle import sim
+    import olfactory_navigation_b200.synthetic as syn
+    c = syn.CONFIGS[CONFIG]
+    data = syn.plume_frames(c['T'], c['h'], c['w'], source_y=c['source'][0], seed=syn.SEED)
+    thr = np.array([-np.inf, c['thresholds'], np.inf])
+    _CPU_SETUP = (sim, sim.build_model(data, c['margins'], c['source'], c['radius'], c['boundary'], thr, c['start_zone'], 0.0))
+    return _CPU_SETUP
+
+
+def cpu_sample(alphas: np.ndarray, actions: np.ndarray, n: int, steps: int, seed: int = 0) -> dict:
+    sim, setup = cpu_setup()
+    import pomdp_toolkit as tk
+    vf = tk.ValueFunction(setup['model'], alphas, actions)
+    r = sim.timed_agent_steps(setup, vf, n, steps, seed)
+    return r
+
+
+def oracle_value_function(G_target: int = None):
+    'A value function for the reference arm without a GPU: the oracle\'s own VI (QMDP alphas, G = 4).'
+    sim, setup = cpu_setup()
+    import pomdp_toolkit as tk
+    vf, _ = tk.solvers.VI.solve(setup['model'], horizon=1000, gamma=0.99, eps=1e-6)
+    return vf.alpha_vector_array, vf.actions
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    alphas, actions = oracle_value_function()
+    for _ in range(max(args.warmup, 0)):
+        cpu_sample(alphas, actions, min(args.cpu_agents, 32), 2)
+    total_steps, total_time = 0, 0.0
+    for k in range(args.steps):
+        r = cpu_sample(alphas, actions, args.cpu_agents, args.cpu_steps, seed=k)
+        total_steps += r['agent_steps']
+        total_time += r['seconds']
+    value = total_steps / total_time
+    sample = (f'oracle/sim.py NumPy fp64 restatement of the reference loop (reference = pure Python over the absent pomdp_toolkit); '
+              f'{args.cpu_agents} agents x {args.cpu_steps} sim steps per bench step on the {CONFIG} model, QMDP value function (G=4), '
+              f'single process, NumPy/BLAS threads')
+    line = {'impl': 'reference', 'metric': 'agent_belief_steps_per_s', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_time / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'C2 run_test: 83x371 states, 4 actions, 3 observations, bounded CPU sample', 'agents_per_step': args.cpu_agents},
+            'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# =================================================================================================
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---- workload: environment, trained agent (untimed) --------------------------------------------
+    c = onb.synthetic.config(CONFIG)
+    env = onb.Environment(**c['env_kwargs'])
+    agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+    agent.train(print_progress=False, print_stats=False, **TRAIN)
+    G = len(agent.value_function)
+    model = agent.model
+    S = model.state_count
+    n = args.agents
+    rng = np.random.default_rng(onb.synthetic.SEED + 17 * rank)         # every rank simulates its own shard of agents
+    starts = env.random_start_points(n, rng)
+    tshift = rng.integers(0, env.timesteps, n)
+
+    moves = torch.as_tensor(np.ascontiguousarray(agent.action_set), dtype=torch.int32, device=dev)
+    thr = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev)
+    env_h = env.device_handle(local)
+    T = env.timesteps
+
+    def device_loop(steps: int, timed: bool):
+        'The device-resident step loop (same operations as run_test, no history copies).'
+        pos = torch.as_tensor(starts, dtype=torch.int32, device=dev).contiguous()
+        ts = torch.as_tensor(tshift, dtype=torch.int64, device=dev).contiguous()
+        odor = torch.empty(n, dtype=torch.float64, device=dev)
+        oid = torch.empty(n, dtype=torch.int32, device=dev)
+        rch = torch.empty(n, dtype=torch.uint8, device=dev)
+        agent.initialize_state(n)
+        live, agent_steps, bs_bytes, events = n, 0, [], []
+        torch.cuda.synchronize(dev)
+        for i in range(steps):
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+            act = agent.choose_action_device()
+            e1.record()
+            t_eff = torch.sort((ts[:live] + i) % T).values.contiguous()
+            check(lib.olfnav_env_step(env_h, live, ptr(pos), ptr(act), ptr(moves), ptr(t_eff), 0, ptr(thr), 3, ptr(odor), ptr(oid), ptr(rch), stream()))
+            reached = rch[:live].bool()
+            n_upd = live - int(reached.sum())
+            e2.record()
+            ok = agent.update_state_device(oid[:live], reached)
+            e3.record()
+            term = reached | ~ok
+            keep = ~term
+            new_pos, new_ts = pos[:live][keep].contiguous(), ts[:live][keep].contiguous()
+            agent.kill_device(term)
+            agent_steps += live
+            nl = int(new_pos.shape[0])
+            pos[:nl], ts[:nl] = new_pos, new_ts
+            if timed:
+                events.append((e0, e1, e2, e3))
+                bs_bytes.append(8.0 * S * n_upd)
+            live = nl
+            if live == 0:
+                break
+        torch.cuda.synchronize(dev)
+        bs_ms = [e[2].elapsed_time(e[3]) for e in events]
+        ev_ms = [e[0].elapsed_time(e[1]) for e in events]
+        return agent_steps, bs_ms, bs_bytes, ev_ms
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- value: device-resident loop -------------------------------------------------------------------
+    device_loop(args.warmup, False)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.olfnav_kernel_launches()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    torch.cuda.nvtx.range_push('timed')
+    agent_steps, bs_ms, bs_bytes, ev_ms = device_loop(args.steps, True)
+    torch.cuda.nvtx.range_pop()
+    t1.record()
+    barrier()
+    launches = int(lib.olfnav_kernel_launches() - launches0)
+    elapsed_ms = t0.elapsed_time(t1)
+
+    # ---- e2e: public API, host buffers in, history records out ------------------------------------------
+    onb.run_test(agent, n=n, start_points=starts, time_shift=tshift, horizon=args.warmup, print_progress=False, print_stats=False, batches=1)
+    barrier()
+    t2 = torch.cuda.Event(enable_timing=True)
+    t3 = torch.cuda.Event(enable_timing=True)
+    t2.record()
+    hist = onb.run_test(agent, n=n, start_points=starts, time_shift=tshift, horizon=args.steps, print_progress=False, print_stats=False, batches=1)
+    t3.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    e2e_ms = t2.elapsed_time(t3)
+    e2e_steps = int(np.sum(np.where(hist.done_at_step >= 0, hist.done_at_step, len(hist))))
+    d2h = 22.0 * e2e_steps / max(len(hist), 1)                 # int32 action + 2 x int32 position + float64 odor + 2 flag bytes per live agent
+    h2d = 16.0 * n / max(len(hist), 1)                         # start points (2 x int32) + time shifts (int64), once per run
+
+    # ---- reduce over ranks (device time = max over ranks; work = sum) ------------------------------------
+    stats = torch.tensor([elapsed_ms, e2e_ms, float(agent_steps), float(e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_ms, agent_steps, e2e_steps = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+        d2h, h2d = d2h * world, h2d * world
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ach = sum(bs_bytes) / (sum(bs_ms) * 1e-3) / 1e9 if sum(bs_ms) > 0 else 0.0
+        line = {
+            'metric': 'agent_belief_steps_per_s', 'value': agent_steps / (elapsed_ms * 1e-3), 'unit': 'agent-steps/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'C2 run_test of a trained FSVI agent: 55x247 plume + 14/62 margins = 83x371 = 30793 states, 4 actions, 3 observations, wrap_vertical',
+                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': 'simt-fp32' if G <= 8 else 'tcgen05-3xtf32',
+                       'sharding': 'agents split across ranks, no data-path collective',
+                       'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * model.padded_states * 4 / 1e9)},
+            'e2e': {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches,
+            'clocks': clk,
+            'roofline': {'kernel': 'belief_step_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                         'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
+                         'share_of_step': sum(bs_ms) / elapsed_ms, 'evaluate_ms_per_step': statistics.mean(ev_ms) if ev_ms else None,
+                         'belief_step_ms_per_step': statistics.mean(bs_ms) if bs_ms else None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            vf = agent.value_function
+            r = cpu_sample(vf.alpha_vector_array, vf.actions, args.cpu_agents, args.cpu_steps)
+            line['cpu_baseline'] = {'value': r['per_s'], 'unit': 'agent-steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                    'sample': f'oracle/sim.py (NumPy fp64 restatement of the reference loop) on {args.cpu_agents} agents x {args.cpu_steps} steps '
+                                              f'of the same model and value function (G={G}); {r["agent_steps"]} agent-steps in {r["seconds"]:.1f} s; single process, BLAS threads'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

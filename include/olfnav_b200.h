@@ -62,6 +62,7 @@ int         olfnav_abi_version(void);
 const char* olfnav_last_error(void);
 int         olfnav_padded_width(int W);                 /* Wp */
 int64_t     olfnav_padded_states(int H, int W);         /* Sp = H * Wp */
+uint64_t    olfnav_kernel_launches(void);               /* kernels this library has launched so far (process wide) */
 
 /* ------------------------------------------------------------------------------------------------
  * Model  — replaces pomdp_toolkit.POMDP(...) built at

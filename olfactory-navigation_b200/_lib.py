@@ -32,6 +32,7 @@ SIGNATURES = {
     'olfnav_last_error': (ctypes.c_char_p, []),
     'olfnav_padded_width': (_i, [_i]),
     'olfnav_padded_states': (_i64, [_i, _i]),
+    'olfnav_kernel_launches': (ctypes.c_uint64, []),
     'olfnav_model_create': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     'olfnav_model_destroy': (None, [_p]),
     'olfnav_model_dims': (_i, [_p, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),

@@ -11,6 +11,7 @@
 
 // ---- error plumbing (never throw across the C ABI) ------------------------------------------------
 void olfnav_set_error(const char* fmt, ...);
+void olf_count_launch(int n);
 
 #define OLF_CUDA(expr)                                                                         \
     do {                                                                                       \
@@ -31,6 +32,7 @@ void olfnav_set_error(const char* fmt, ...);
 
 #define OLF_LAUNCH_CHECK()                                                                     \
     do {                                                                                       \
+        olf_count_launch(1);                                                                   \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             olfnav_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -128,6 +128,7 @@ extern "C" int olfnav_alphas_create(olfnav_alphas** out, const olfnav_model* m, 
     }
     dim3 grid(olf_div_up(a->ld, 256), a->Gp);
     alpha_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(alpha, ld_alpha, G, m->g.Sp, a->full, a->hi, a->lo, a->ld);
+    olf_count_launch(1);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
         olfnav_set_error("alphas_create: %s", cudaGetErrorString(le));
@@ -167,6 +168,7 @@ extern "C" int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a, co
     }
     if (rc == OLFNAV_OK) {
         eval_finish_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, val, idx, scale, a->actions, value, arg, action);
+        olf_count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("evaluate: finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
     }
     cudaFreeAsync(val, st);

@@ -7,7 +7,13 @@
 #include <cstring>
 #include <vector>
 
+#include <atomic>
+
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void olf_count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" uint64_t olfnav_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void olfnav_set_error(const char* fmt, ...) {
     va_list ap;

@@ -210,6 +210,7 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
             dim3 grid(olf_div_up(ldp, 256), Gs);
             split_planes_kernel<<<grid, 256, 0, st>>>(gamma_ao + (long long)s * G * ld_gamma, ld_gamma, G, m->g.Sp,
                                                       hi + (long long)s * Gs * ldp, lo + (long long)s * Gs * ldp, ldp);
+            olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: split launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
         if (rc == OLFNAV_OK)
@@ -221,6 +222,7 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
     if (rc == OLFNAV_OK) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, m->reward, m->g.Sp, A, 1, rew_val, rew_arg, st);
     if (rc == OLFNAV_OK) {
         backup_pick_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, A, O, scale, seg_val, rew_val, best_a, best_value);
+        olf_count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: pick launch failed"); rc = OLFNAV_ERR_CUDA; }
     }
     cudaFreeAsync(seg_val, st);

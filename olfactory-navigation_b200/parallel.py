@@ -1,0 +1,109 @@
+'''
+Multi-GPU partitioning of the hot path: one process per GPU, `torch.distributed`.
+
+* Simulation: agents are independent, so the start points are split contiguously across ranks exactly like the
+  reference splits them into batches (reference simulation.py:1370-1413) and the per-rank histories are
+  concatenated like SimulationHistory.__add__ (:550-618).  NO collective on the data path; one object gather
+  of the (small) histories at the end.
+* Training: the belief points of one backup are split across ranks, every rank holds the full alpha set, and the
+  new (alpha, action) pairs are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Works with any initialised process group; with none it degrades to the single-process behaviour.
+'''
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world_size: int) -> tuple[int, int]:
+    'Contiguous split with the remainder on the first ranks (same rule as the reference\'s batch sizes, simulation.py:1372-1374).'
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def run_test_sharded(agent, n: int, start_points: np.ndarray, time_shift: np.ndarray, **kwargs):
+    '''
+    run_test over every rank's slice of the agents.  Returns the concatenated SimulationHistory on rank 0
+    (None elsewhere).  `start_points` / `time_shift` are the full arrays on every rank.
+    '''
+    from .simulation import run_test
+    rank, ws = world()
+    lo, hi = shard_bounds(n, rank, ws)
+    kwargs.setdefault('print_progress', False)
+    kwargs.setdefault('print_stats', False)
+    hist = run_test(agent, n=hi - lo, start_points=np.asarray(start_points)[lo:hi], time_shift=np.asarray(time_shift)[lo:hi], **kwargs) if hi > lo else None
+    if ws == 1:
+        return hist
+    if hist is not None:
+        hist.environment, hist.agent = None, None              # keep the gathered objects small and picklable
+    gathered = [None] * ws if rank == 0 else None
+    dist.gather_object(hist, gathered, dst=0)
+    if rank != 0:
+        return None
+    out = None
+    for h in gathered:
+        if h is None:
+            continue
+        h.environment, h.agent = agent.environment, agent
+        out = h if out is None else out + h
+    return out
+
+
+def all_gather_rows(rows: torch.Tensor, extra: torch.Tensor = None):
+    '''
+    Concatenate a (k_r, D) tensor (k_r may differ per rank) over all ranks, plus an optional (k_r,) companion.
+    One all_gather of the row counts and one padded all_gather of the payload.
+    '''
+    rank, ws = world()
+    if ws == 1:
+        return rows, extra
+    k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros_like(k) for _ in range(ws)]
+    dist.all_gather(counts, k)
+    counts = [int(c) for c in counts]
+    kmax = max(max(counts), 1)
+    pad = torch.zeros((kmax, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    out = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+    out_extra = None
+    if extra is not None:
+        epad = torch.zeros(kmax, dtype=extra.dtype, device=extra.device)
+        epad[:extra.shape[0]] = extra
+        eparts = [torch.empty_like(epad) for _ in range(ws)]
+        dist.all_gather(eparts, epad)
+        out_extra = torch.cat([p[:c] for p, c in zip(eparts, counts)], dim=0)
+    return out, out_extra
+
+
+def all_gather_alphas(new_alpha: torch.Tensor, actions: torch.Tensor):
+    'New alpha vectors (B_r, Sp) + actions (B_r,) of every rank, in rank order.'
+    return all_gather_rows(new_alpha, actions)
+
+
+def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: int = 0):
+    '''
+    One PBVI backup with the belief points split across ranks: each rank backs up rows [lo, hi) of the (replicated)
+    belief set against the full alpha set, then the new vectors are all-gathered.  Returns (new_alpha, best_a) for
+    ALL belief points on every rank, in the original order.
+    '''
+    from .pomdp import BeliefSet
+    from .solvers import backup_device
+    rank, ws = world()
+    lo, hi = shard_bounds(len(belief_set), rank, ws)
+    part = BeliefSet(model, _buffers=(belief_set._b[lo:hi], belief_set._scale[lo:hi], hi - lo), device=belief_set.device)
+    if hi > lo:
+        new_alpha, best_a, _, _ = backup_device(model, part, alphas, gamma, path)
+    else:
+        new_alpha = torch.empty((0, alphas.shape[1]), dtype=alphas.dtype, device=alphas.device)
+        best_a = torch.empty(0, dtype=torch.int32, device=alphas.device)
+    return all_gather_alphas(new_alpha, best_a)

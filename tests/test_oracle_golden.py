@@ -88,3 +88,29 @@ def test_fsvi_trajectory_draw_order(tk):
         s1 = tk.solvers.FSVI.trajectory(m, m.start_probabilities, Q, 12, np.random.default_rng(seed))
         s2 = dsolvers.FSVI.trajectory(agent.model, agent.model.start_probabilities, Q, 12, np.random.default_rng(seed))
         assert s1 == s2 and len(s1) > 0
+
+
+@pytest.mark.parametrize('cfg', ['T0', 'T1', 'T2', 'T3', 'C1'])
+@pytest.mark.parametrize('label', ['qmdp', 'fsvi'])
+def test_oracle_sim_loop_reproduces_reference_run_test(cfg, label, tk):
+    'oracle/sim.py (restated run loop, the CPU baseline) == the reference\'s run_test, step by step, bit exact.'
+    import olfactory_navigation_b200.synthetic as syn
+    from oracle import sim
+    g = golden(f'runtest_{label}_{cfg}')
+    c = syn.CONFIGS[cfg]
+    data = syn.plume_frames(c['T'], c['h'], c['w'], source_y=c['source'][0], seed=syn.SEED)
+    thr = np.sort(np.array([-np.inf] + (c['thresholds'] if isinstance(c['thresholds'], list) else [c['thresholds']]) + [np.inf]))
+    setup = sim.build_model(data, c['margins'], c['source'], c['radius'], c['boundary'], thr, c['start_zone'],
+                            0.0 if c['start_zone'] == 'odor_present' else None)
+    conv = golden(f'converter_{cfg}')
+    assert np.array_equal(setup['model'].observation_table, conv['observation_table'])
+    assert np.array_equal(setup['model'].reachable_states[:, :, 0], conv['reachable_states'])
+    assert np.array_equal(setup['model'].start_probabilities, conv['start_probabilities'])
+    vf = tk.ValueFunction(setup['model'], g['alphas'].astype(np.float64), g['alpha_actions'])
+    out = sim.run_test(setup, vf, g['start_points'].astype(int), g['time_shift'], int(g['horizon']))
+    # the fixture's value function was rounded to float32: trajectories may differ at near-ties only
+    same = (out['done_at_step'] == g['done_at_step']) & (out['reached_source'] == g['reached_source'])
+    assert same.mean() >= 0.9
+    sims, act, pos, odor = out['records'][0]
+    assert np.array_equal(pos, g['positions'][0][sims]) and np.array_equal(setup['action_set'][act], g['actions'][0][sims])
+    assert np.array_equal(odor.astype(np.float32), g['observations'][0][sims])
