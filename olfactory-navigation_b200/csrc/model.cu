@@ -63,6 +63,15 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
     OLF_CUDA(cudaGetDeviceCount(&ndev));
     OLF_REQUIRE(device >= 0 && device < ndev, "model_create: device %d of %d", device, ndev);
     OLF_CUDA(cudaSetDevice(device));
+    // Stream-ordered temporaries (cudaMallocAsync in evaluate / backup_select) must not be handed back to the OS at every
+    // synchronisation: with the default release threshold (0) each simulation step would re-map its scratch memory.
+    if (!(getenv("OLFNAV_NO_POOL_RETAIN") && getenv("OLFNAV_NO_POOL_RETAIN")[0] == '1')) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
 
     olfnav_model* m = new (std::nothrow) olfnav_model();
     if (!m) { olfnav_set_error("model_create: out of host memory"); return OLFNAV_ERR_NOMEM; }

@@ -148,7 +148,7 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));   // power of two >= 32
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
@@ -277,7 +277,7 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t aph = (ccount >> 1) & 1;
                     mbar_wait(bar_tfull(acc), aph);
                     tc_fence_after();
-                    if constexpr (BN >= 128) {       // narrower loads: 128 running sums already fill the register file
+                    if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
 #pragma unroll
                         for (int c0 = 0; c0 < BN; c0 += 16) {
                             uint32_t v[16];
@@ -375,7 +375,9 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax: bad segment layout");
     OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax: empty problem");
 
-    const int BN = rows_b <= 32 ? 32 : (rows_b <= 64 ? 64 : 128);   // <= 128: the epilogue keeps BN FP32 partial sums in registers
+    // Tile width: exactly ceil16(rows_b) when it fits one tile (no MMA work on padding columns), else 128-wide tiles.
+    // <= 128 because the epilogue keeps BN FP32 partial sums in registers.
+    const int BN = rows_b <= 128 ? ((rows_b + 15) & ~15) : 128;
     GemmParams p;
     p.n_rows = (int)n_rows; p.K = K; p.rows_b = rows_b;
     p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
@@ -391,9 +393,15 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     if (rc != OLFNAV_OK) return rc;
 
     const int grid = p.num_m_tiles < sm_count ? p.num_m_tiles : sm_count;
+    // stages: as many as fit ~220 KB of shared memory (stage = 32 KB of A planes + 2 B planes of BN x 128 B)
     switch (BN) {
+        case 16:  return launch<16, 6>(tA, tBh, tBl, p, grid, st);
         case 32:  return launch<32, 5>(tA, tBh, tBl, p, grid, st);
+        case 48:  return launch<48, 4>(tA, tBh, tBl, p, grid, st);
         case 64:  return launch<64, 4>(tA, tBh, tBl, p, grid, st);
+        case 80:  return launch<80, 4>(tA, tBh, tBl, p, grid, st);
+        case 96:  return launch<96, 3>(tA, tBh, tBl, p, grid, st);
+        case 112: return launch<112, 3>(tA, tBh, tBl, p, grid, st);
         default:  return launch<128, 3>(tA, tBh, tBl, p, grid, st);
     }
 }

