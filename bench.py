@@ -182,50 +182,26 @@ def run_ours(args) -> None:
     starts = env.random_start_points(n, rng)
     tshift = rng.integers(0, env.timesteps, n)
 
-    moves = torch.as_tensor(np.ascontiguousarray(agent.action_set), dtype=torch.int32, device=dev)
-    thr = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev)
-    env_h = env.device_handle(local)
-    T = env.timesteps
+    from olfactory_navigation_b200 import simulation as onb_sim
 
     def device_loop(steps: int, timed: bool):
-        'The device-resident step loop (same operations as run_test, no history copies).'
-        pos = torch.as_tensor(starts, dtype=torch.int32, device=dev).contiguous()
-        ts = torch.as_tensor(tshift, dtype=torch.int64, device=dev).contiguous()
-        odor = torch.empty(n, dtype=torch.float64, device=dev)
-        oid = torch.empty(n, dtype=torch.int32, device=dev)
-        rch = torch.empty(n, dtype=torch.uint8, device=dev)
-        agent.initialize_state(n)
-        live, agent_steps, bs_bytes, events = n, 0, [], []
+        '''
+        The device-resident step loop: the same `olfnav_sim_step` call per step as run_test (policy -> environment step ->
+        compaction plan -> fused belief update), start points already uploaded, no history records copied out.
+        Kernel times come from CUDA events recorded by the library on the launching stream around the policy and the
+        fused belief update.
+        '''
+        timing = [] if timed else None
+        common = dict(environment=env, time_loop=True, horizon=steps, initialization_values={}, reward_discount=0.99,
+                      distance_metric='l1', print_progress=False)
+        hist = onb_sim._run_single(agent, n, starts, tshift, record=False, timing=timing, **common)
         torch.cuda.synchronize(dev)
-        for i in range(steps):
-            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            e0.record()
-            act = agent.choose_action_device()
-            e1.record()
-            t_eff = torch.sort((ts[:live] + i) % T).values.contiguous()
-            check(lib.olfnav_env_step(env_h, live, ptr(pos), ptr(act), ptr(moves), ptr(t_eff), 0, ptr(thr), 3, ptr(odor), ptr(oid), ptr(rch), stream()))
-            reached = rch[:live].bool()
-            n_upd = live - int(reached.sum())
-            e2.record()
-            ok = agent.update_state_device(oid[:live], reached)
-            e3.record()
-            term = reached | ~ok
-            keep = ~term
-            new_pos, new_ts = pos[:live][keep].contiguous(), ts[:live][keep].contiguous()
-            agent.kill_device(term)
-            agent_steps += live
-            nl = int(new_pos.shape[0])
-            pos[:nl], ts[:nl] = new_pos, new_ts
-            if timed:
-                events.append((e0, e1, e2, e3))
-                bs_bytes.append(8.0 * S * n_upd)
-            live = nl
-            if live == 0:
-                break
-        torch.cuda.synchronize(dev)
-        bs_ms = [e[2].elapsed_time(e[3]) for e in events]
-        ev_ms = [e[0].elapsed_time(e[1]) for e in events]
-        return agent_steps, bs_ms, bs_bytes, ev_ms
+        bs_ms, ev_ms, bs_bytes = [], [], []
+        for (live, evs, counts) in (timing or []):
+            ev_ms.append(evs[0].elapsed_time(evs[1]))
+            bs_ms.append(evs[2].elapsed_time(evs[3]))
+            bs_bytes.append(8.0 * S * counts)            # survivors actually updated by the kernel
+        return hist._agent_steps, bs_ms, bs_bytes, ev_ms
 
     def barrier():
         torch.cuda.synchronize(dev)

@@ -185,6 +185,43 @@ int olfnav_env_step(const olfnav_env* e, int64_t n,
                     double* odor /* [dev] n */, int32_t* obs_id /* [dev] n */, uint8_t* reached /* [dev] n */,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One whole simulation step — the body of run_test's loop, simulation.py:1452-1497 — with no host
+ * synchronisation inside.  All pointers [dev]; arrays hold >= n entries unless noted.
+ *   policy      alphas != NULL: argmax_g b.alpha_g (agents/pbvi_agent.py:741); NULL: infotaxis (agents/infotaxis_agent.py:244-301)
+ *   env         move / observe / source check / discretise                      (environment.py:554-769, agent.py:401-439)
+ *   update      survivors (agents that did not reach the source) are updated into rows 0..m-1 of b_out / scale_out,
+ *               pos_out / ts_out hold their positions / time shifts in the same order (replaces arrays[~to_terminate] and
+ *               belief_array[~kill], simulation.py:1495-1497, agents/pbvi_agent.py:810-811)
+ *   counts      [0] = m survivors, [1] = failed updates among them, [2] = ended recordings among them (time_loop = 0), [3] = n
+ *   records     indexed like the INPUT agents: act (action id), rec_pos (n x 2, after the move), rec_odor, rec_reached,
+ *               rec_term (reached | failed | ended).  term_c[j] (j < m) flags survivors that must still be dropped.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct olfnav_sim_step_args {
+    const float* b_in; float* b_out; int64_t ld;
+    const float* scale_in; float* scale_out;
+    const int32_t* pos_in; int32_t* pos_out;          /* n x 2 (y, x) */
+    const int64_t* ts_in; int64_t* ts_out;            /* time shifts */
+    int64_t n; int64_t step;
+    const int32_t* moves;                             /* A x 2 */
+    const double* thresholds; int32_t n_thr;
+    int32_t time_mode;                                /* 0: each agent its own time; 1: the reference's sorted-time indexing */
+    int32_t time_loop;                                /* 1: recordings loop for ever (run_test default) */
+    int32_t eval_path;                                /* see olfnav_evaluate */
+    int32_t* act; int32_t* obs_id; int32_t* src_rows; int32_t* act_c; int32_t* obs_c;
+    uint8_t* ok; uint8_t* at_end; uint8_t* term_c;
+    int32_t* hist;                                    /* T + 1 ints, time_mode 1 only */
+    float* eval_val; int32_t* eval_idx;               /* alphas != NULL only */
+    int32_t* rec_pos; double* rec_odor; uint8_t* rec_reached; uint8_t* rec_term;
+    int32_t* counts;                                  /* 4 ints */
+    /* optional cudaEvent_t handles (NULL = none), recorded on `stream`: after the policy kernels, before and after the
+     * fused belief update — lets a caller time the dominant kernels live without breaking the single call apart */
+    void* ev_policy_end; void* ev_update_begin; void* ev_update_end;
+} olfnav_sim_step_args;
+
+int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas /* NULL = infotaxis */, const olfnav_env* e,
+                    const olfnav_sim_step_args* args /* [host] */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

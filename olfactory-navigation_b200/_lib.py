@@ -55,6 +55,31 @@ SIGNATURES = {
     'olfnav_env_step': (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i, _p, _p, _p, _p]),
 }
 
+
+
+class SimStepArgs(ctypes.Structure):
+    'Mirror of olfnav_sim_step_args (include/olfnav_b200.h).'
+    _fields_ = [
+        ('b_in', _p), ('b_out', _p), ('ld', _i64),
+        ('scale_in', _p), ('scale_out', _p),
+        ('pos_in', _p), ('pos_out', _p),
+        ('ts_in', _p), ('ts_out', _p),
+        ('n', _i64), ('step', _i64),
+        ('moves', _p),
+        ('thresholds', _p), ('n_thr', ctypes.c_int32),
+        ('time_mode', ctypes.c_int32), ('time_loop', ctypes.c_int32), ('eval_path', ctypes.c_int32),
+        ('act', _p), ('obs_id', _p), ('src_rows', _p), ('act_c', _p), ('obs_c', _p),
+        ('ok', _p), ('at_end', _p), ('term_c', _p),
+        ('hist', _p),
+        ('eval_val', _p), ('eval_idx', _p),
+        ('rec_pos', _p), ('rec_odor', _p), ('rec_reached', _p), ('rec_term', _p),
+        ('counts', _p),
+        ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
+    ]
+
+
+SIGNATURES['olfnav_sim_step'] = (_i, [_p, _p, _p, ctypes.POINTER(SimStepArgs), _p])
+
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)   # AttributeError here = the library does not export a declared symbol
     _fn.restype = _res

@@ -40,6 +40,7 @@ struct StepArgs {
     int n;
     int stagger;
     int inplace;
+    const int* n_dev;      // optional device-side row count: CTAs with blockIdx.x >= *n_dev exit (grid sized by an upper bound)
 };
 
 template <bool INPLACE>
@@ -51,6 +52,7 @@ belief_step_kernel(const StepArgs p, const __grid_constant__ Geom g) {
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int i = blockIdx.x;
+    if (p.n_dev && i >= *p.n_dev) return;
     const long long src = p.src_rows ? p.src_rows[i] : i;
     const long long dst = p.dst_rows ? p.dst_rows[i] : i;
     int a = p.act[i], o = p.obs[i];
@@ -236,6 +238,7 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
 
     const int tid = threadIdx.x;
     const int i = blockIdx.x;
+    if (p.n_dev && i >= *p.n_dev) return;
     const long long src = p.src_rows ? p.src_rows[i] : i;
     const long long dst = p.dst_rows ? p.dst_rows[i] : i;
     int a = p.act[i], o = p.obs[i];
@@ -461,6 +464,13 @@ extern "C" int olfnav_belief_init(const olfnav_model* m, float* b, int64_t ld, i
 extern "C" int olfnav_belief_step(const olfnav_model* m, const float* b_in, float* b_out, int64_t ld, int64_t n,
                                   const int32_t* act, const int32_t* obs, const int32_t* src_rows, const int32_t* dst_rows,
                                   const float* scale_in, float* scale_out, uint8_t* ok, void* stream) {
+    return olf_belief_step_launch(m, b_in, b_out, ld, n, act, obs, src_rows, dst_rows, scale_in, scale_out, ok, nullptr, stream);
+}
+
+// n = upper bound of the rows to update (grid size); n_dev (optional) = device-side exact count.
+int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_out, int64_t ld, int64_t n,
+                           const int32_t* act, const int32_t* obs, const int32_t* src_rows, const int32_t* dst_rows,
+                           const float* scale_in, float* scale_out, uint8_t* ok, const int* n_dev, void* stream) {
     OLF_REQUIRE(m && b_in && b_out && act && obs && scale_out && ok, "belief_step: null argument");
     OLF_REQUIRE(ld >= m->g.Sp && (ld % 4) == 0, "belief_step: ld must be >= Sp and a multiple of 4");
     OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL, "belief_step: n out of range");
@@ -479,6 +489,7 @@ extern "C" int olfnav_belief_step(const olfnav_model* m, const float* b_in, floa
     static const int stagger = [] { const char* e = getenv("OLFNAV_BELIEF_STAGGER"); return e ? atoi(e) : 4; }();
     p.stagger = stagger;
     p.inplace = inplace ? 1 : 0;
+    p.n_dev = n_dev;
     // v2 (TMA ring) whenever a grid row fits one stage; OLFNAV_BELIEF_V1=1 forces the register-streaming v1 kernel
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_BELIEF_V1"); return e && e[0] == '1'; }();
     if (!force_v1 && m->g.W4 <= BS2_THREADS * BS2_UNROLL) {

@@ -122,3 +122,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 static inline int olf_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points shared between translation units ---------------------------------------------
+int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_out, int64_t ld, int64_t n,
+                           const int32_t* act, const int32_t* obs, const int32_t* src_rows, const int32_t* dst_rows,
+                           const float* scale_in, float* scale_out, uint8_t* ok, const int* n_dev, void* stream);
+// evaluate with caller-provided scratch (val, idx: n entries each); any of value / arg / action may be NULL
+int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n, const float* scale,
+                      float* val, int* idx, float* value, int32_t* arg, int32_t* action, int path, cudaStream_t st);

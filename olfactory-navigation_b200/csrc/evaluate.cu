@@ -146,6 +146,18 @@ extern "C" void olfnav_alphas_destroy(olfnav_alphas* a) {
     delete a;
 }
 
+int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n, const float* scale,
+                      float* val, int* idx, float* value, int32_t* arg, int32_t* action, int path, cudaStream_t st) {
+    if (path == 0) path = (a->G <= 8) ? 1 : 2;
+    int rc;
+    if (path == 1) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, a->full, a->ld, 1, a->G, val, idx, st);
+    else           rc = olf_umma_segmax(b, ld, n, m->g.Sp, a->hi, a->lo, a->ld, a->Gp, 1, a->G, a->Gp, val, idx, m->sm_count, st);
+    if (rc != OLFNAV_OK) return rc;
+    eval_finish_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, val, idx, scale, a->actions, value, arg, action);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
 extern "C" int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n,
                                const float* scale, float* value, int32_t* arg, int32_t* action, int path, void* stream) {
     OLF_REQUIRE(m && a && b, "evaluate: null argument");
@@ -154,23 +166,11 @@ extern "C" int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a, co
     if (n == 0) return OLFNAV_OK;
     OLF_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (path == 0) path = (a->G <= 8) ? 1 : 2;
-
     float* val = nullptr;
     int* idx = nullptr;
     OLF_CUDA(cudaMallocAsync((void**)&val, (size_t)n * sizeof(float), st));
     OLF_CUDA(cudaMallocAsync((void**)&idx, (size_t)n * sizeof(int), st));
-    int rc;
-    if (path == 1) {
-        rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, a->full, a->ld, 1, a->G, val, idx, st);
-    } else {
-        rc = olf_umma_segmax(b, ld, n, m->g.Sp, a->hi, a->lo, a->ld, a->Gp, 1, a->G, a->Gp, val, idx, m->sm_count, st);
-    }
-    if (rc == OLFNAV_OK) {
-        eval_finish_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, val, idx, scale, a->actions, value, arg, action);
-        olf_count_launch(1);
-        if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("evaluate: finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
-    }
+    const int rc = olf_evaluate_into(m, a, b, ld, n, scale, val, idx, value, arg, action, path, st);
     cudaFreeAsync(val, st);
     cudaFreeAsync(idx, st);
     return rc;

@@ -283,40 +283,71 @@ def _run_batches(agent, n, start_points, time_shift, batches, **kw) -> Simulatio
 
 
 def _run_single(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
-                reward_discount, distance_metric, print_progress) -> SimulationHistory:
+                reward_discount, distance_metric, print_progress, record: bool = True, timing: list = None) -> SimulationHistory:
+    '''
+    One batch, device resident.  Per step: ONE C-ABI call (olfnav_sim_step: policy -> environment step -> compaction
+    plan -> fused belief update) and one 16-byte read-back of the survivor counts; the O(N) history record of the
+    step is copied to pinned host memory on a side stream while the next step runs.
+    '''
+    from ._lib import SimStepArgs
+    from .agents.pbvi_agent import BeliefSimulationMixin
     from .pomdp import current_device
+    import ctypes
+    if not isinstance(agent, BeliefSimulationMixin):
+        return _run_generic(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
+                            reward_discount, distance_metric, print_progress)
     device = current_device()
     dev = torch.device('cuda', device)
     env_h = environment.device_handle(device)
     copy_stream = torch.cuda.Stream(device=dev)
-
-    # host -> device, once
-    pos = torch.as_tensor(np.ascontiguousarray(start_points), dtype=torch.int32, device=dev).contiguous()
-    tshift = torch.as_tensor(np.ascontiguousarray(time_shift), dtype=torch.int64, device=dev).contiguous()
-    thresholds = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev).contiguous()
-    n_thr = int(thresholds.numel())
-    moves = torch.as_tensor(np.ascontiguousarray(agent.action_set), dtype=torch.int32, device=dev).contiguous()
+    main = torch.cuda.current_stream(dev)
 
     agent.initialize_state(n, **initialization_values)
+    model = agent.model
+    model_h = model.handle(device)
+    vf = getattr(agent, 'value_function', None)
+    is_infotaxis = not hasattr(agent, 'value_function')
+    alphas_h = None if is_infotaxis else vf.handle(device)
     hist = SimulationHistory(start_points=start_points, environment=environment, agent=agent, time_shift=time_shift,
                              horizon=horizon, reward_discount=reward_discount, distance_metric=distance_metric, used_gpu=True)
 
-    odor = torch.empty(n, dtype=torch.float64, device=dev)
-    obs_id = torch.empty(n, dtype=torch.int32, device=dev)
-    reached_u8 = torch.empty(n, dtype=torch.uint8, device=dev)
-    pending = []        # (event, pinned buffers) of records still in flight
+    # host -> device, once
+    cap = max(n, 1)
+    pos = [torch.as_tensor(np.ascontiguousarray(start_points), dtype=torch.int32, device=dev).contiguous().reshape(cap, 2) if n else torch.zeros((1, 2), dtype=torch.int32, device=dev),
+           torch.empty((cap, 2), dtype=torch.int32, device=dev)]
+    ts = [torch.as_tensor(np.ascontiguousarray(time_shift), dtype=torch.int64, device=dev).contiguous() if n else torch.zeros(1, dtype=torch.int64, device=dev),
+          torch.empty(cap, dtype=torch.int64, device=dev)]
+    thresholds = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev).contiguous()
+    moves = torch.as_tensor(np.ascontiguousarray(agent.action_set), dtype=torch.int32, device=dev).contiguous()
     T = environment.timesteps
+
+    def i32(k=cap):
+        return torch.empty(k, dtype=torch.int32, device=dev)
+
+    def u8(k=cap):
+        return torch.empty(k, dtype=torch.uint8, device=dev)
+    act, obs_id, src_rows, act_c, obs_c = i32(), i32(), i32(), i32(), i32()
+    ok, at_end, term_c = u8(), u8(), u8()
+    hist_t = i32(T + 1)
+    eval_val, eval_idx = torch.empty(cap, dtype=torch.float32, device=dev), i32()
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    counts_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+    # two record sets so that step i+1 can run while step i's record is still being copied out
+    recs = [dict(pos=torch.empty((cap, 2), dtype=torch.int32, device=dev), odor=torch.empty(cap, dtype=torch.float64, device=dev),
+                 reached=u8(), term=u8(), act=i32()) for _ in range(2)]
+    rec_free = [None, None]            # event: the record set has been copied out
+    pending = []
 
     def flush(upto: int) -> None:
         while len(pending) > upto:
-            ev, (h_act, h_pos, h_odor, h_flags), m = pending.pop(0)
+            ev, (h_act, h_pos, h_odor, h_reached, h_term), m_rec = pending.pop(0)
             ev.synchronize()
-            fl = h_flags.numpy()
-            hist.add_step(actions=h_act.numpy()[:m].astype(np.int64), next_positions=h_pos.numpy()[:m].astype(np.int64),
-                          observations=h_odor.numpy()[:m], reached_source=fl[0, :m].astype(bool), interupt=fl[1, :m].astype(bool),
-                          action_is_id=True)
+            hist.add_step(actions=h_act.numpy()[:m_rec].astype(np.int64), next_positions=h_pos.numpy()[:m_rec].astype(np.int64),
+                          observations=h_odor.numpy()[:m_rec], reached_source=h_reached.numpy()[:m_rec].astype(bool),
+                          interupt=h_term.numpy()[:m_rec].astype(bool), action_is_id=True)
 
-    n_live = n
+    args = SimStepArgs()
+    n_live, cur = n, 0
     iterator = range(horizon)
     if print_progress:
         try:
@@ -325,53 +356,117 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         except Exception:
             pass
     for i in iterator:
-        act_ids = agent.choose_action_device()                                   # (n_live,) int32
-        if environment.reference_time_quirk:
-            # agent i observes the frame of the i-th smallest (time_shift + i) % T (see Environment.reference_time_quirk)
-            t_eff, t_step = torch.sort((tshift[:n_live] + i) % T).values.contiguous(), 0
-        else:
-            t_eff, t_step = tshift, i
-        with torch.cuda.device(device):
-            check(lib.olfnav_env_step(env_h, n_live, ptr(pos), ptr(act_ids), ptr(moves), ptr(t_eff), t_step,
-                                      ptr(thresholds), n_thr, ptr(odor), ptr(obs_id), ptr(reached_u8), stream()))
-        reached = reached_u8[:n_live].bool()
-        ok = agent.update_state_device(obs_id[:n_live], reached)
-        if time_loop:
-            term = reached | ~ok
-        else:
-            term = reached | ~ok | ((tshift + (i + 1)) >= T)
-
-        # record (device -> pinned host, asynchronously on the side stream)
-        flags = torch.stack([reached, term]).to(torch.uint8)
-        bufs = (torch.empty(n_live, dtype=torch.int32, pin_memory=True), torch.empty((n_live, 2), dtype=torch.int32, pin_memory=True),
-                torch.empty(n_live, dtype=torch.float64, pin_memory=True), torch.empty((2, n_live), dtype=torch.uint8, pin_memory=True))
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            bufs[0].copy_(act_ids[:n_live], non_blocking=True)
-            bufs[1].copy_(pos[:n_live], non_blocking=True)
-            bufs[2].copy_(odor[:n_live], non_blocking=True)
-            bufs[3].copy_(flags, non_blocking=True)
-            for t in (act_ids, flags):
-                t.record_stream(copy_stream)
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-        pending.append((done, bufs, n_live))
-
-        keep = ~term
-        new_pos = pos[:n_live][keep].contiguous()
-        new_ts = tshift[:n_live][keep].contiguous()
-        agent.kill_device(term)
-        # pos/odor are overwritten by the next step: the record copy must have read them first
-        torch.cuda.current_stream(dev).wait_event(done)
-        n_live = int(new_pos.shape[0])           # the one host sync of the step
-        pos[:n_live] = new_pos
-        tshift[:n_live] = new_ts
-        flush(2)
         if n_live == 0:
             break
+        r = recs[i & 1]
+        if rec_free[i & 1] is not None:
+            main.wait_event(rec_free[i & 1])
+        b_cur, b_nxt = agent._bufs[agent._cur], agent._bufs[1 - agent._cur]
+        s_cur, s_nxt = agent._scales[agent._cur], agent._scales[1 - agent._cur]
+        args.b_in, args.b_out, args.ld = b_cur.data_ptr(), b_nxt.data_ptr(), b_cur.stride(0)
+        args.scale_in, args.scale_out = s_cur.data_ptr(), s_nxt.data_ptr()
+        args.pos_in, args.pos_out = pos[cur].data_ptr(), pos[1 - cur].data_ptr()
+        args.ts_in, args.ts_out = ts[cur].data_ptr(), ts[1 - cur].data_ptr()
+        args.n, args.step = n_live, i
+        args.moves, args.thresholds, args.n_thr = moves.data_ptr(), thresholds.data_ptr(), int(thresholds.numel())
+        args.time_mode = 1 if environment.reference_time_quirk else 0
+        args.time_loop = 1 if time_loop else 0
+        args.eval_path = int(getattr(agent, 'gemm_path', 0))
+        args.act, args.obs_id, args.src_rows, args.act_c, args.obs_c = r['act'].data_ptr(), obs_id.data_ptr(), src_rows.data_ptr(), act_c.data_ptr(), obs_c.data_ptr()
+        args.ok, args.at_end, args.term_c = ok.data_ptr(), at_end.data_ptr(), term_c.data_ptr()
+        args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
+        args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
+        args.counts = counts.data_ptr()
+        if timing is not None:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            for e in evs:
+                e.record(main)                                  # creates the underlying cudaEvent_t handles
+            args.ev_policy_end, args.ev_update_begin, args.ev_update_end = evs[1].cuda_event, evs[2].cuda_event, evs[3].cuda_event
+            evs[0].record(main)
+        with torch.cuda.device(device):
+            check(lib.olfnav_sim_step(model_h, alphas_h, env_h, ctypes.byref(args), stream()))
+        counts_host.copy_(counts, non_blocking=True)
+        step_done = torch.cuda.Event()
+        step_done.record(main)
+        if timing is not None:
+            evs[4].record(main)
+
+        # record of this step -> pinned host memory on the side stream
+        bufs = None if not record else (torch.empty(n_live, dtype=torch.int32, pin_memory=True), torch.empty((n_live, 2), dtype=torch.int32, pin_memory=True),
+                torch.empty(n_live, dtype=torch.float64, pin_memory=True), torch.empty(n_live, dtype=torch.uint8, pin_memory=True),
+                torch.empty(n_live, dtype=torch.uint8, pin_memory=True))
+        with torch.cuda.stream(copy_stream) if record else _null_context():
+          if record:
+            copy_stream.wait_event(step_done)
+            bufs[0].copy_(r['act'][:n_live], non_blocking=True)
+            bufs[1].copy_(r['pos'][:n_live], non_blocking=True)
+            bufs[2].copy_(r['odor'][:n_live], non_blocking=True)
+            bufs[3].copy_(r['reached'][:n_live], non_blocking=True)
+            bufs[4].copy_(r['term'][:n_live], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(copy_stream)
+            rec_free[i & 1] = copied
+            pending.append((copied, bufs, n_live))
+        hist._agent_steps = getattr(hist, '_agent_steps', 0) + n_live
+
+        step_done.synchronize()                                  # the one host sync of the step
+        m, n_fail, n_end = int(counts_host[0]), int(counts_host[1]), int(counts_host[2])
+        if timing is not None:
+            timing.append((n_live, evs, m))
+        agent._cur, agent._n_live, agent._action_ids, agent._dropped = 1 - agent._cur, m, None, None
+        cur = 1 - cur
+        if n_fail or n_end:
+            # rare: some survivors must still go (impossible update / end of the recording): explicit compaction
+            keep = ~term_c[:m].bool()
+            rows = torch.nonzero(keep).flatten()
+            k = int(rows.numel())
+            if k:
+                pos[1 - cur][:k] = pos[cur][:m][rows]
+                ts[1 - cur][:k] = ts[cur][:m][rows]
+            cur = 1 - cur
+            agent.kill_device(~keep)
+            m = k
+        n_live = m
+        flush(2)
         if print_progress and hasattr(iterator, 'set_postfix'):
             iterator.set_postfix({'done ': f' {n - n_live}/{n}'})
     flush(0)
+    if n_live == 0:
+        agent._bufs = None
+    return hist
+
+
+class _null_context:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _run_generic(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
+                 reward_discount, distance_metric, print_progress) -> SimulationHistory:
+    '''
+    Host-driven loop for agents that only implement the reference's NumPy protocol (custom Agent subclasses):
+    the literal step order of the reference's run_test (simulation.py:1452-1497).
+    '''
+    pos, ts = np.array(start_points), np.array(time_shift)
+    agent.initialize_state(n, **initialization_values)
+    hist = SimulationHistory(start_points=start_points, environment=environment, agent=agent, time_shift=time_shift,
+                             horizon=horizon, reward_discount=reward_discount, distance_metric=distance_metric, used_gpu=False)
+    for i in range(horizon):
+        action = agent.choose_action()
+        pos = environment.move(pos=pos, movement=action)
+        observation = environment.get_observation(pos=pos, time=(ts + i))
+        reached = environment.source_reached(pos)
+        ok = agent.update_state(action=action, observation=observation, source_reached=reached)
+        if ok is None:
+            ok = np.ones(len(reached), dtype=bool)
+        at_end = (ts + i + 1) >= (math.inf if time_loop else environment.timesteps)
+        term = reached | at_end | ~np.asarray(ok, dtype=bool)
+        hist.add_step(actions=action, next_positions=pos, observations=observation, reached_source=reached, interupt=term)
+        pos, ts = pos[~term], ts[~term]
+        agent.kill(simulations_to_kill=term)
+        if len(pos) == 0:
+            break
     return hist
