@@ -24,6 +24,7 @@
 #include "umma_gemm.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
@@ -39,8 +40,33 @@ struct GemmParams {
     int n_seg, seg_len, seg_stride;
     float* out_val;
     int* out_arg;
+    unsigned long long* ws;      // packed (value, first index) keys combined with atomicMax when a row's columns span several units
     int num_m_tiles, num_n_tiles, num_k_blocks;
+    int num_units, group_w;      // work units = (m tile, n tile); n tiles are visited in groups of group_w so that the CTAs of one
+                                 // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
+    int raw_hi;                  // 1: leave the raw FP32 A tile as the "hi" operand (the tensor core ignores the low 13 mantissa bits)
 };
+
+// unit id -> (m tile, n tile)
+__device__ __forceinline__ void unit_to_tile(const GemmParams& p, int u, int& mt, int& nt) {
+    const int per_group = p.num_m_tiles * p.group_w;
+    int g = u / per_group;
+    const int n_groups = (p.num_n_tiles + p.group_w - 1) / p.group_w;
+    if (g >= n_groups) g = n_groups - 1;
+    const int rem = u - g * per_group;
+    const int wg = min(p.group_w, p.num_n_tiles - g * p.group_w);
+    mt = rem / wg;
+    nt = g * p.group_w + (rem - mt * wg);
+}
+
+// order-preserving float -> uint32, packed with the inverted column index: atomicMax keeps the largest value and, among equal
+// values, the smallest index (np.argmax's first maximum)
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+    unsigned u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)idx);
+}
+
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,17 +201,17 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
-                for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(bar_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_full(s), A_TILE_BYTES + 2 * L::B_TILE_BYTES);
-                        tma_load_2d(a_hi(s), &tmA, kb * BK, mt * BM, bar_full(s));
-                        tma_load_2d(b_hi(s), &tmBhi, kb * BK, nt * BN, bar_full(s));
-                        tma_load_2d(b_lo(s), &tmBlo, kb * BK, nt * BN, bar_full(s));
-                    }
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                int mt, nt;
+                unit_to_tile(p, u, mt, nt);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_full(s), A_TILE_BYTES + 2 * L::B_TILE_BYTES);
+                    tma_load_2d(a_hi(s), &tmA, kb * BK, mt * BM, bar_full(s));
+                    tma_load_2d(b_hi(s), &tmBhi, kb * BK, nt * BN, bar_full(s));
+                    tma_load_2d(b_lo(s), &tmBlo, kb * BK, nt * BN, bar_full(s));
                 }
             }
         }
@@ -193,123 +219,137 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32<BN>();
         uint32_t it = 0, ccount = 0;
-        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
-            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-                for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
-                    const int acc = ccount & 1;
-                    const uint32_t aph = (ccount >> 1) & 1;
-                    mbar_wait(bar_tempty(acc), aph ^ 1);
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tempty(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const int kb1 = min(KB, kb0 + KCHUNK);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_ready(s), ph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * BN;
-                    const int kb1 = min(KB, kb0 + KCHUNK);
-                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(bar_ready(s), ph);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
-                            const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
+                    if (lane == 0) {
+                        const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
+                        const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
 #pragma unroll
-                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                                const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
-                                tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-                                tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
-                                tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
-                            }
-                            tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
-                            if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
+                            tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+                            tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
                         }
-                        __syncwarp();
+                        tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
+                        if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================== A transform: raw FP32 -> (hi in place, lo) =====================
+        // All eight 16-byte pieces of a thread are loaded before the first one is split, so the shared-memory latency is paid once
+        // per stage.  The split is elementwise, so the 128B swizzle of the tile is irrelevant here.
         const int t = threadIdx.x - 128;
+        constexpr int PIECES = A_TILE_BYTES / 16 / 128;
         uint32_t it = 0;
-        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
-            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_full(s), ph);
-                    const uint32_t ah = a_hi(s), al = a_lo(s);
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(bar_full(s), ph);
+                float4* ah = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES) + t;
+                float4* al = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES + A_TILE_BYTES) + t;
+                float4 v[PIECES];
 #pragma unroll
-                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
-                        const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
-                        float4 v;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ah + off));
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                        l.x = __uint_as_float(__float_as_uint(v.x - h.x) & 0xffffe000u);
-                        l.y = __uint_as_float(__float_as_uint(v.y - h.y) & 0xffffe000u);
-                        l.z = __uint_as_float(__float_as_uint(v.z - h.z) & 0xffffe000u);
-                        l.w = __uint_as_float(__float_as_uint(v.w - h.w) & 0xffffe000u);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(ah + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(al + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
-                    mbar_arrive(bar_ready(s));
+                for (int i = 0; i < PIECES; ++i) v[i] = ah[128 * i];
+#pragma unroll
+                for (int i = 0; i < PIECES; ++i) {
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+                    l.x = __uint_as_float(__float_as_uint(v[i].x - h.x) & 0xffffe000u);
+                    l.y = __uint_as_float(__float_as_uint(v[i].y - h.y) & 0xffffe000u);
+                    l.z = __uint_as_float(__float_as_uint(v[i].z - h.z) & 0xffffe000u);
+                    l.w = __uint_as_float(__float_as_uint(v[i].w - h.w) & 0xffffe000u);
+                    if (!p.raw_hi) ah[128 * i] = h;
+                    al[128 * i] = l;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+                mbar_arrive(bar_ready(s));
             }
         }
     } else if (warp >= 8) {
         // ===================== epilogue: FP32 register accumulation + segmented max / argmax =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const bool direct = p.ws == nullptr;         // one n tile covers all columns: write the results directly
         uint32_t ccount = 0;
-        for (int mt = blockIdx.x; mt < p.num_m_tiles; mt += gridDim.x) {
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int mt, nt;
+            unit_to_tile(p, u, mt, nt);
             const long long row = (long long)mt * BM + q * 32 + lane;
             const bool row_ok = row < p.n_rows;
-            int cur_seg = 0, r = 0;                  // current segment and index inside its stride
+            const int col0 = nt * BN;
+            int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;   // current segment and index inside its stride
             float best = -INFINITY;
             int best_idx = 0;
-            for (int nt = 0; nt < p.num_n_tiles; ++nt) {
-                float sum[BN];
+            bool dirty = false;
+            float sum[BN];
 #pragma unroll
-                for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-                for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
-                    const int acc = ccount & 1;
-                    const uint32_t aph = (ccount >> 1) & 1;
-                    mbar_wait(bar_tfull(acc), aph);
-                    tc_fence_after();
-                    if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
+            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tfull(acc), aph);
+                tc_fence_after();
+                if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
 #pragma unroll
-                        for (int c0 = 0; c0 < BN; c0 += 16) {
-                            uint32_t v[16];
-                            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int c0 = 0; c0 < BN; c0 += 32) {
-                            uint32_t v[32];
-                            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-                        }
+                        for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
                     }
-                    tc_fence_before();
-                    mbar_arrive(bar_tempty(acc));
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < BN; ++j) {
-                    const float x = sum[j];
-                    if (r < p.seg_len && cur_seg < p.n_seg && x > best) { best = x; best_idx = r; }
-                    if (++r == p.seg_stride) {
-                        if (row_ok && cur_seg < p.n_seg) {
-                            p.out_val[row * p.n_seg + cur_seg] = best;
-                            p.out_arg[row * p.n_seg + cur_seg] = best_idx;
-                        }
-                        r = 0; ++cur_seg; best = -INFINITY; best_idx = 0;
+                tc_fence_before();
+                mbar_arrive(bar_tempty(acc));
+            }
+            auto flush = [&]() {
+                if (row_ok && cur_seg < p.n_seg) {
+                    if (direct) {
+                        p.out_val[row * p.n_seg + cur_seg] = best;
+                        p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                    } else if (dirty) {
+                        atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
                     }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                const float x = sum[j];
+                if (r < p.seg_len && cur_seg < p.n_seg) {
+                    dirty = true;
+                    if (x > best) { best = x; best_idx = r; }
+                }
+                if (++r == p.seg_stride) {
+                    flush();
+                    r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
                 }
             }
+            if (r != 0 && !direct) flush();          // the segment continues in another unit
         }
     }
 
@@ -319,6 +359,19 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// ws -> (value, first index); entries no unit touched stay (-inf, 0)
+__global__ void segmax_decode_kernel(long long n, const unsigned long long* __restrict__ ws, float* __restrict__ out_val,
+                                     int* __restrict__ out_arg) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = ws[i];
+    if (k == 0ull) { out_val[i] = -INFINITY; out_arg[i] = 0; return; }
+    unsigned u = (unsigned)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    out_val[i] = __uint_as_float(u);
+    out_arg[i] = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -385,6 +438,16 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     p.num_m_tiles = olf_div_up(n_rows, BM);
     p.num_n_tiles = olf_div_up(rows_b, BN);
     p.num_k_blocks = olf_div_up(K, BK);
+    p.num_units = p.num_m_tiles * p.num_n_tiles;
+    p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
+    static const int raw_hi = [] { const char* e = getenv("OLFNAV_GEMM_RAWHI"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.raw_hi = raw_hi;
+    p.ws = nullptr;
+    const size_t n_out = (size_t)n_rows * n_seg;
+    if (p.num_n_tiles > 1) {
+        OLF_CUDA(cudaMallocAsync((void**)&p.ws, n_out * sizeof(unsigned long long), st));
+        OLF_CUDA(cudaMemsetAsync(p.ws, 0, n_out * sizeof(unsigned long long), st));
+    }
 
     CUtensorMap tA, tBh, tBl;
     int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM);
@@ -392,16 +455,25 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b, (uint64_t)ldb * 4, BN);
     if (rc != OLFNAV_OK) return rc;
 
-    const int grid = p.num_m_tiles < sm_count ? p.num_m_tiles : sm_count;
+    const int grid = p.num_units < sm_count ? p.num_units : sm_count;
     // stages: as many as fit ~220 KB of shared memory (stage = 32 KB of A planes + 2 B planes of BN x 128 B)
     switch (BN) {
-        case 16:  return launch<16, 6>(tA, tBh, tBl, p, grid, st);
-        case 32:  return launch<32, 5>(tA, tBh, tBl, p, grid, st);
-        case 48:  return launch<48, 4>(tA, tBh, tBl, p, grid, st);
-        case 64:  return launch<64, 4>(tA, tBh, tBl, p, grid, st);
-        case 80:  return launch<80, 4>(tA, tBh, tBl, p, grid, st);
-        case 96:  return launch<96, 3>(tA, tBh, tBl, p, grid, st);
-        case 112: return launch<112, 3>(tA, tBh, tBl, p, grid, st);
-        default:  return launch<128, 3>(tA, tBh, tBl, p, grid, st);
+        case 16:  rc = launch<16, 6>(tA, tBh, tBl, p, grid, st); break;
+        case 32:  rc = launch<32, 5>(tA, tBh, tBl, p, grid, st); break;
+        case 48:  rc = launch<48, 4>(tA, tBh, tBl, p, grid, st); break;
+        case 64:  rc = launch<64, 4>(tA, tBh, tBl, p, grid, st); break;
+        case 80:  rc = launch<80, 4>(tA, tBh, tBl, p, grid, st); break;
+        case 96:  rc = launch<96, 3>(tA, tBh, tBl, p, grid, st); break;
+        case 112: rc = launch<112, 3>(tA, tBh, tBl, p, grid, st); break;
+        default:  rc = launch<128, 3>(tA, tBh, tBl, p, grid, st); break;
     }
+    if (p.ws) {
+        if (rc == OLFNAV_OK) {
+            segmax_decode_kernel<<<olf_div_up((int64_t)n_out, 256), 256, 0, st>>>((long long)n_out, p.ws, out_val, out_arg);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax: decode kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        cudaFreeAsync(p.ws, st);
+    }
+    return rc;
 }
