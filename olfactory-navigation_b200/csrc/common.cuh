@@ -60,6 +60,12 @@ struct olfnav_model {
     float* start;      // [Sp]
     uint8_t* end_mask; // [Sp]
     int sm_count;
+    // infotaxis "pull" tables as GEMM operand planes (TF32 hi / lo, see evaluate.cu): row a*(O+1)+o = O_o(R_a(s)) for o < O,
+    // row a*(O+1)+O = C(R_a(s)); pull_rows = A*(O+1), stored rows rounded up to 16, row stride pull_ld (multiple of 32)
+    float* pull_hi;
+    float* pull_lo;
+    int pull_rows, pull_rows_p;
+    int64_t pull_ld;
 };
 
 struct olfnav_alphas {

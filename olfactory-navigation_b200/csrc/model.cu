@@ -115,6 +115,29 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
             }
         }
 
+    // infotaxis pull tables (TF32 hi / lo planes): row a*(O+1)+o = O_o(R_a(s)), row a*(O+1)+O = C(R_a(s))
+    m->pull_rows = A * (O + 1);
+    m->pull_rows_p = (m->pull_rows + 15) & ~15;
+    m->pull_ld = (Sp + 31) & ~31;
+    std::vector<float> h_phi((size_t)m->pull_rows_p * m->pull_ld, 0.f), h_plo((size_t)m->pull_rows_p * m->pull_ld, 0.f);
+    auto split = [](float v, float& h, float& l) {
+        uint32_t u; memcpy(&u, &v, 4); u &= 0xffffe000u; memcpy(&h, &u, 4);
+        float d = v - h; memcpy(&u, &d, 4); u &= 0xffffe000u; memcpy(&l, &u, 4);
+    };
+    for (int a = 0; a < A; ++a) {
+        const int ae = per_action ? a : 0;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int sp = y * g.Wp + x;
+                const int sp2 = bmove(y, g.moves[a][0], H, wy) * g.Wp + bmove(x, g.moves[a][1], W, wx);
+                for (int o = 0; o <= O; ++o) {
+                    const float v = (o < O) ? h_obs[((size_t)ae * O + o) * Sp + sp2] : h_ent[(size_t)ae * Sp + sp2];
+                    const size_t at = (size_t)(a * (O + 1) + o) * m->pull_ld + sp;
+                    split(v, h_phi[at], h_plo[at]);
+                }
+            }
+    }
+
     cudaError_t e = cudaSuccess;
     auto up = [&](void** dptr, const void* src, size_t bytes) {
         if (e != cudaSuccess) return;
@@ -126,6 +149,8 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
     up((void**)&m->reward, h_rew.data(), h_rew.size() * sizeof(float));
     up((void**)&m->start, h_start.data(), h_start.size() * sizeof(float));
     up((void**)&m->end_mask, h_end.data(), h_end.size());
+    up((void**)&m->pull_hi, h_phi.data(), h_phi.size() * sizeof(float));
+    up((void**)&m->pull_lo, h_plo.data(), h_plo.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         olfnav_set_error("model_create: %s", cudaGetErrorString(e));
@@ -140,6 +165,7 @@ extern "C" void olfnav_model_destroy(olfnav_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
+    cudaFree(m->pull_hi); cudaFree(m->pull_lo);
     delete m;
 }
 

@@ -25,6 +25,7 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -44,6 +45,8 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles, num_k_blocks;
     int num_units, group_w;      // work units = (m tile, n tile); n tiles are visited in groups of group_w so that the CTAs of one
                                  // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
+    float* out_store;            // != NULL: store mode, out_store[row * out_ld + col] = product (col < rows_b); no max / argmax
+    long long out_ld;
     int raw_hi;                  // 1: leave the raw FP32 A tile as the "hi" operand (the tensor core ignores the low 13 mantissa bits)
 };
 
@@ -327,6 +330,14 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(bar_tempty(acc));
             }
+            if (p.out_store) {
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < BN; ++j)
+                        if (col0 + j < p.rows_b) p.out_store[row * p.out_ld + col0 + j] = sum[j];
+                }
+                continue;
+            }
             auto flush = [&]() {
                 if (row_ok && cur_seg < p.n_seg) {
                     if (direct) {
@@ -419,41 +430,31 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl
 
 }  // namespace
 
-int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
-                    int rows_b, int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count,
-                    cudaStream_t st) {
-    OLF_REQUIRE(A && B_hi && B_lo && out_val && out_arg, "umma_segmax: null argument");
-    OLF_REQUIRE((lda % 4) == 0 && (((uintptr_t)A) & 15) == 0, "umma_segmax: A must be 16-byte aligned with lda %% 4 == 0");
-    OLF_REQUIRE((ldb % 32) == 0 && ldb >= K, "umma_segmax: ldb must be a multiple of 32 and >= K");
-    OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax: bad segment layout");
-    OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax: empty problem");
-
+static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
+                    int rows_b_stored, GemmParams p, int sm_count, cudaStream_t st) {
     // Tile width: exactly ceil16(rows_b) when it fits one tile (no MMA work on padding columns), else 128-wide tiles.
     // <= 128 because the epilogue keeps BN FP32 partial sums in registers.
-    const int BN = rows_b <= 128 ? ((rows_b + 15) & ~15) : 128;
-    GemmParams p;
-    p.n_rows = (int)n_rows; p.K = K; p.rows_b = rows_b;
-    p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
-    p.out_val = out_val; p.out_arg = out_arg;
+    const int BN = rows_b_stored <= 128 ? ((rows_b_stored + 15) & ~15) : 128;
+    p.n_rows = (int)n_rows; p.K = K;
     p.num_m_tiles = olf_div_up(n_rows, BM);
-    p.num_n_tiles = olf_div_up(rows_b, BN);
+    p.num_n_tiles = olf_div_up(rows_b_stored, BN);
     p.num_k_blocks = olf_div_up(K, BK);
     p.num_units = p.num_m_tiles * p.num_n_tiles;
     p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
     static const int raw_hi = [] { const char* e = getenv("OLFNAV_GEMM_RAWHI"); return (e && e[0] == '1') ? 1 : 0; }();
     p.raw_hi = raw_hi;
     p.ws = nullptr;
-    const size_t n_out = (size_t)n_rows * n_seg;
-    if (p.num_n_tiles > 1) {
+    const size_t n_out = (size_t)n_rows * p.n_seg;
+    if (!p.out_store && p.num_n_tiles > 1) {
         OLF_CUDA(cudaMallocAsync((void**)&p.ws, n_out * sizeof(unsigned long long), st));
         OLF_CUDA(cudaMemsetAsync(p.ws, 0, n_out * sizeof(unsigned long long), st));
     }
 
     CUtensorMap tA, tBh, tBl;
     int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM);
-    if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b, (uint64_t)ldb * 4, BN);
-    if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b, (uint64_t)ldb * 4, BN);
-    if (rc != OLFNAV_OK) return rc;
+    if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
+    if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
+    if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
 
     const int grid = p.num_units < sm_count ? p.num_units : sm_count;
     // stages: as many as fit ~220 KB of shared memory (stage = 32 KB of A planes + 2 B planes of BN x 128 B)
@@ -469,11 +470,42 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     }
     if (p.ws) {
         if (rc == OLFNAV_OK) {
-            segmax_decode_kernel<<<olf_div_up((int64_t)n_out, 256), 256, 0, st>>>((long long)n_out, p.ws, out_val, out_arg);
+            segmax_decode_kernel<<<olf_div_up((int64_t)n_out, 256), 256, 0, st>>>((long long)n_out, p.ws, p.out_val, p.out_arg);
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax: decode kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
         cudaFreeAsync(p.ws, st);
     }
     return rc;
+}
+
+int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
+                    int rows_b, int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count,
+                    cudaStream_t st) {
+    OLF_REQUIRE(A && B_hi && B_lo && out_val && out_arg, "umma_segmax: null argument");
+    OLF_REQUIRE((lda % 4) == 0 && (((uintptr_t)A) & 15) == 0, "umma_segmax: A must be 16-byte aligned with lda %% 4 == 0");
+    OLF_REQUIRE((ldb % 32) == 0 && ldb >= K, "umma_segmax: ldb must be a multiple of 32 and >= K");
+    OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax: bad segment layout");
+    OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax: empty problem");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows_b = rows_b;
+    p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
+    p.out_val = out_val; p.out_arg = out_arg;
+    return umma_run(A, lda, n_rows, K, B_hi, B_lo, ldb, rows_b, p, sm_count, st);
+}
+
+int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
+                   int rows_b, float* out, int64_t out_ld, int sm_count, cudaStream_t st) {
+    OLF_REQUIRE(A && B_hi && B_lo && out, "umma_store: null argument");
+    OLF_REQUIRE((lda % 4) == 0 && (((uintptr_t)A) & 15) == 0, "umma_store: A must be 16-byte aligned with lda %% 4 == 0");
+    OLF_REQUIRE((ldb % 32) == 0 && ldb >= K, "umma_store: ldb must be a multiple of 32 and >= K");
+    OLF_REQUIRE(rows_b >= 1 && rows_b <= 128 && out_ld >= rows_b, "umma_store: 1 <= rows_b <= 128 and out_ld >= rows_b");
+    OLF_REQUIRE(n_rows > 0 && K > 0, "umma_store: empty problem");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows_b = rows_b;
+    p.n_seg = 1; p.seg_len = rows_b; p.seg_stride = (rows_b + 15) & ~15;
+    p.out_store = out; p.out_ld = out_ld;
+    return umma_run(A, lda, n_rows, K, B_hi, B_lo, ldb, (rows_b + 15) & ~15, p, sm_count, st);
 }

@@ -13,3 +13,9 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K,
                     const float* B_hi, const float* B_lo, int64_t ldb, int rows_b,
                     int n_seg, int seg_len, int seg_stride,
                     float* out_val, int* out_arg, int sm_count, cudaStream_t st);
+
+// Plain product with the same split precision: out[i*out_ld + c] = A[i,:] . B[c,:] for c < rows_b (rows_b <= 128, stored
+// rows of B rounded up to 16).  Used by the infotaxis choice (belief x pull tables).
+int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K,
+                   const float* B_hi, const float* B_lo, int64_t ldb, int rows_b,
+                   float* out, int64_t out_ld, int sm_count, cudaStream_t st);
