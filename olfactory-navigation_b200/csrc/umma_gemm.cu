@@ -47,6 +47,8 @@ struct GemmParams {
                                  // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
     float* out_store;            // != NULL: store mode, out_store[row * out_ld + col] = product (col < rows_b); no max / argmax
     long long out_ld;
+    int pair;                    // the producer issues the A loads of `pair` consecutive k-blocks together (same DRAM pages)
+    int dbg;                     // timing experiments only (OLFNAV_GEMM_DBG bitmask): 1 no B loads, 2 no MMA issue, 8 no TMEM loads
     int raw_hi;                  // 1: leave the raw FP32 A tile as the "hi" operand (the tensor core ignores the low 13 mantissa bits)
 };
 
@@ -100,6 +102,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// One lane of the (converged) warp.  With elect.sync ptxas knows the guarded region runs in a single thread and emits the
+// uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR) straight-line; guarded by `lane == 0` it wraps every one of them in
+// an ELECT / BRA.U.ANY loop that costs ~110 cycles per tcgen05.mma (measured, scripts/umma_rate_bench.cu).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -114,6 +124,19 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (TS form): lane = row of A, 8 consecutive 32-bit columns = the K = 8 slice
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -202,19 +225,28 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t it = 0;
             for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
                 int mt, nt;
                 unit_to_tile(p, u, mt, nt);
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_empty(s), ph ^ 1);
-                    mbar_expect_tx(bar_full(s), A_TILE_BYTES + 2 * L::B_TILE_BYTES);
-                    tma_load_2d(a_hi(s), &tmA, kb * BK, mt * BM, bar_full(s));
-                    tma_load_2d(b_hi(s), &tmBhi, kb * BK, nt * BN, bar_full(s));
-                    tma_load_2d(b_lo(s), &tmBlo, kb * BK, nt * BN, bar_full(s));
+                const int pair = (p.pair > 1 && p.pair <= STAGES / 2) ? p.pair : 1;
+                for (int kb0 = 0; kb0 < KB; kb0 += pair) {
+                    const int np = min(pair, KB - kb0);
+                    // A first, for all k-blocks of the group: their 128-byte pieces are adjacent in every belief row
+                    for (int j = 0; j < np; ++j) {
+                        const int s = (it + j) % STAGES;
+                        const uint32_t ph = ((it + j) / STAGES) & 1;
+                        mbar_wait(bar_empty(s), ph ^ 1);
+                        mbar_expect_tx(bar_full(s), A_TILE_BYTES + ((p.dbg & 1) ? 0 : 2 * L::B_TILE_BYTES));
+                        tma_load_2d(a_hi(s), &tmA, (kb0 + j) * BK, mt * BM, bar_full(s));
+                    }
+                    for (int j = 0; j < np && !(p.dbg & 1); ++j) {
+                        const int s = (it + j) % STAGES;
+                        tma_load_2d(b_hi(s), &tmBhi, (kb0 + j) * BK, nt * BN, bar_full(s));
+                        tma_load_2d(b_lo(s), &tmBlo, (kb0 + j) * BK, nt * BN, bar_full(s));
+                    }
+                    it += np;
                 }
             }
         }
@@ -235,17 +267,19 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(bar_ready(s), ph);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one_sync()) {
                         const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
                         const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        for (int kk = 0; kk < BK / UMMA_K && !(p.dbg & 2) && !((p.dbg & 4) && (kb & 1)); ++kk) {
                             const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
                             tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                            if (p.raw_hi == 3) continue;             // timing experiment only: 1xTF32
                             tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
                             tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
                         }
-                        tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
+                        if (p.dbg & 16) mbar_arrive(bar_empty(s));   // timing experiment only: frees the stage without waiting for the MMAs
+                        else tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
                         if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
                     }
                     __syncwarp();
@@ -267,6 +301,11 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float4* ah = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES) + t;
                 float4* al = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES + A_TILE_BYTES) + t;
                 float4 v[PIECES];
+                if (p.raw_hi == 2) {      // timing experiment only: no split at all (results are 1xTF32)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(bar_ready(s));
+                    continue;
+                }
 #pragma unroll
                 for (int i = 0; i < PIECES; ++i) v[i] = ah[128 * i];
 #pragma unroll
@@ -310,7 +349,8 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t aph = (ccount >> 1) & 1;
                 mbar_wait(bar_tfull(acc), aph);
                 tc_fence_after();
-                if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
+                if (p.dbg & 8) {
+                } else if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
 #pragma unroll
                     for (int c0 = 0; c0 < BN; c0 += 16) {
                         uint32_t v[16];
@@ -372,6 +412,246 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
+// ============================================================================================================
+// v3: A operand in TENSOR MEMORY.  Measured on B200 (scripts/umma_rate_bench.cu, OLFNAV_GEMM_DBG experiments): with both
+// operands in shared memory the kernel is bound by the 128 B/clk shared-memory port — TMA writes, the hi/lo transform's
+// loads and stores AND the tensor core's own operand reads (4 KB of A per K = 8 step for FP32 operands) all go through it.
+// Here the transform warps read the raw FP32 A tile once (conflict-free row reads of the 128B-swizzled tile), split it in
+// registers and write hi and lo straight into tensor memory (tcgen05.st); the MMAs take A from TMEM and only B from shared
+// memory.  Shared memory per stage shrinks to the raw A tile + the two B planes, so more stages fit.
+//   TMEM columns: [0, 2*BN) two accumulator buffers, [A_BASE + 64*s, +32) hi and (+32, +64) lo of stage s.
+template <int BN, int STAGES>
+struct SmemLayoutTS {
+    static constexpr int B_TILE_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int A_BASE = BN <= 64 ? 128 : 256;
+    static_assert(A_BASE + 64 * STAGES <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+    using L = SmemLayoutTS<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+    auto a_raw = [&](int s) { return base + s * L::STAGE_BYTES; };
+    auto b_hi = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES; };
+    auto b_lo = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES + L::B_TILE_BYTES; };
+    const uint32_t bars = base + L::BAR_OFFSET;
+    auto bar_full = [&](int s) { return bars + 8 * s; };
+    auto bar_ready = [&](int s) { return bars + 8 * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8 * (2 * STAGES + s); };
+    auto bar_tfull = [&](int a) { return bars + 8 * (3 * STAGES + a); };
+    auto bar_tempty = [&](int a) { return bars + 8 * (3 * STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * (3 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 512;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBlo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 128); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int KB = p.num_k_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one_sync()) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                int mt, nt;
+                unit_to_tile(p, u, mt, nt);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_full(s), A_TILE_BYTES + 2 * L::B_TILE_BYTES);
+                    tma_load_2d(a_raw(s), &tmA, kb * BK, mt * BM, bar_full(s));
+                    tma_load_2d(b_hi(s), &tmBhi, kb * BK, nt * BN, bar_full(s));
+                    tma_load_2d(b_lo(s), &tmBlo, kb * BK, nt * BN, bar_full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32<BN>();
+        uint32_t it = 0, ccount = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tempty(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const int kb1 = min(KB, kb0 + KCHUNK);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_ready(s), ph);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t ah = tmem_base + L::A_BASE + 64 * s, al = ah + 32;
+                        const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
+                            tc_mma_tf32_ts(d_tmem, ah + kk * UMMA_K, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                            tc_mma_tf32_ts(d_tmem, al + kk * UMMA_K, dbh + adv, idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, ah + kk * UMMA_K, dbl + adv, idesc, 1u);
+                        }
+                        tc_commit(bar_empty(s));                 // frees the stage (shared memory and its TMEM slot) once these MMAs retire
+                        if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== A transform: raw FP32 row (shared memory) -> hi / lo (tensor memory) =====================
+        // Thread t owns row t of the tile (= TMEM lane t; warp w may touch lanes 32 (w % 4) .. +31).  The tile is 128B-swizzled:
+        // the 16-byte piece c of row r sits at piece c ^ (r & 7), which makes the row-wise reads of a quarter warp conflict free.
+        const int t = threadIdx.x - 128;
+        const uint8_t* rowp = gbase + t * 128;
+        const int sw = t & 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(bar_full(s), ph);
+                // (the stage's TMEM slot is free: bar_empty(s) completed before the producer refilled the stage)
+                tc_fence_after();
+                const uint8_t* src = rowp + s * L::STAGE_BYTES;
+                const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * s;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 v[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const float4*>(src + (((half * 4 + c) ^ sw) << 4));
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t hb = __float_as_uint(x[e]) & 0xffffe000u;
+                            h[4 * c + e] = hb;
+                            l[4 * c + e] = __float_as_uint(x[e] - __uint_as_float(hb)) & 0xffffe000u;
+                        }
+                    }
+                    tc_st16(th + half * 16, h);
+                    tc_st16(th + 32 + half * 16, l);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_ready(s));
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue: FP32 register accumulation + segmented max / argmax =====================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const bool direct = p.ws == nullptr;         // one n tile covers all columns: write the results directly
+        uint32_t ccount = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int mt, nt;
+            unit_to_tile(p, u, mt, nt);
+            const long long row = (long long)mt * BM + q * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            const int col0 = nt * BN;
+            int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;
+            float best = -INFINITY;
+            int best_idx = 0;
+            bool dirty = false;
+            float sum[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tfull(acc), aph);
+                tc_fence_after();
+                if constexpr (BN >= 112 || (BN % 32) != 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 16) {
+                        uint32_t v[16];
+                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty(acc));
+            }
+            if (p.out_store) {
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < BN; ++j)
+                        if (col0 + j < p.rows_b) p.out_store[row * p.out_ld + col0 + j] = sum[j];
+                }
+                continue;
+            }
+            auto flush = [&]() {
+                if (row_ok && cur_seg < p.n_seg) {
+                    if (direct) {
+                        p.out_val[row * p.n_seg + cur_seg] = best;
+                        p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                    } else if (dirty) {
+                        atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
+                    }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                const float x = sum[j];
+                if (r < p.seg_len && cur_seg < p.n_seg) {
+                    dirty = true;
+                    if (x > best) { best = x; best_idx = r; }
+                }
+                if (++r == p.seg_stride) {
+                    flush();
+                    r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
+                }
+            }
+            if (r != 0 && !direct) flush();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ws -> (value, first index); entries no unit touched stay (-inf, 0)
 __global__ void segmax_decode_kernel(long long n, const unsigned long long* __restrict__ ws, float* __restrict__ out_val,
                                      int* __restrict__ out_arg) {
@@ -402,7 +682,8 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows) {
+int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows,
+                CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { olfnav_set_error("umma: cuTensorMapEncodeTiled not available"); return OLFNAV_ERR_CUDA; }
     cuuint64_t dims[2] = {inner, outer};
@@ -410,7 +691,7 @@ int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t out
     cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { olfnav_set_error("umma: cuTensorMapEncodeTiled failed (%d)", (int)r); return OLFNAV_ERR_CUDA; }
     return OLFNAV_OK;
 }
@@ -428,6 +709,19 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl
     return OLFNAV_OK;
 }
 
+template <int BN, int STAGES>
+int launch_ts(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl, const GemmParams& p, int grid, cudaStream_t st) {
+    using L = SmemLayoutTS<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        OLF_CUDA(cudaFuncSetAttribute(umma_ts_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    umma_ts_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
 }  // namespace
 
 static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const float* B_hi, const float* B_lo, int64_t ldb,
@@ -441,8 +735,10 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     p.num_k_blocks = olf_div_up(K, BK);
     p.num_units = p.num_m_tiles * p.num_n_tiles;
     p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
-    static const int raw_hi = [] { const char* e = getenv("OLFNAV_GEMM_RAWHI"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int raw_hi = [] { const char* e = getenv("OLFNAV_GEMM_RAWHI"); return e ? atoi(e) : 0; }();
     p.raw_hi = raw_hi;
+    static const int dbg = [] { const char* e = getenv("OLFNAV_GEMM_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
     p.ws = nullptr;
     const size_t n_out = (size_t)n_rows * p.n_seg;
     if (!p.out_store && p.num_n_tiles > 1) {
@@ -451,12 +747,35 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     }
 
     CUtensorMap tA, tBh, tBl;
-    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM);
+    // A streams from HBM in 128-byte pieces per belief row (row stride ~123 KB): let L2 fetch 256 B per miss, so that every second
+    // k-block of a row is an L2 hit and the DRAM row-activate rate halves (OLFNAV_GEMM_APROMO = 64 | 128 | 256, default 256)
+    static const CUtensorMapL2promotion a_promo = [] {
+        const char* e = getenv("OLFNAV_GEMM_APROMO");
+        const int v = e ? atoi(e) : 256;
+        return v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    }();
+    static const int pair_env = [] { const char* e = getenv("OLFNAV_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    p.pair = pair_env;
+    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM, a_promo);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
 
     const int grid = p.num_units < sm_count ? p.num_units : sm_count;
+    static const bool force_ss = [] { const char* e = getenv("OLFNAV_GEMM_SS"); return e && e[0] == '1'; }();
+    if (!force_ss) {
+        // A in tensor memory: stage = 16 KB raw A + 2 B planes of BN x 128 B; TMEM holds 64 columns of hi / lo per stage
+        switch (BN) {
+            case 16:  rc = launch_ts<16, 6>(tA, tBh, tBl, p, grid, st); break;
+            case 32:  rc = launch_ts<32, 6>(tA, tBh, tBl, p, grid, st); break;
+            case 48:  rc = launch_ts<48, 6>(tA, tBh, tBl, p, grid, st); break;
+            case 64:  rc = launch_ts<64, 6>(tA, tBh, tBl, p, grid, st); break;
+            case 80:  rc = launch_ts<80, 4>(tA, tBh, tBl, p, grid, st); break;
+            case 96:  rc = launch_ts<96, 4>(tA, tBh, tBl, p, grid, st); break;
+            case 112: rc = launch_ts<112, 4>(tA, tBh, tBl, p, grid, st); break;
+            default:  rc = launch_ts<128, 4>(tA, tBh, tBl, p, grid, st); break;
+        }
+    } else
     // stages: as many as fit ~220 KB of shared memory (stage = 32 KB of A planes + 2 B planes of BN x 128 B)
     switch (BN) {
         case 16:  rc = launch<16, 6>(tA, tBh, tBl, p, grid, st); break;
