@@ -47,6 +47,9 @@ def parse():
     ap.add_argument('--cpu-agents', type=int, default=256)
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-backup', action='store_true')
+    ap.add_argument('--backup-points', type=int, default=10_000)
+    ap.add_argument('--backup-alphas', type=int, default=512)
     return ap.parse_args()
 
 
@@ -153,6 +156,49 @@ def run_reference(args) -> None:
 
 
 # =================================================================================================
+def measure_backup(onb, model, world, rank, dev, args):
+    '''
+    One PBVI backup (Gamma_{a,o} build -> belief x Gamma tcgen05 GEMM with per-(a,o) argmax -> alpha assembly) of B belief points
+    against G alpha vectors; the belief points are split across the ranks and the new alpha vectors all-gathered (strong scaling:
+    B is the whole job's).  Device time over 3 repetitions after 2 warm-ups, max over ranks.
+    '''
+    import torch
+    import torch.distributed as dist
+    from olfactory_navigation_b200 import parallel
+    B, G = args.backup_points, args.backup_alphas
+    rng = np.random.default_rng(99)                                   # same belief points and alphas on every rank
+    bs = onb.BeliefSet(model, B)
+    for _ in range(6):
+        bs = bs.update(rng.integers(0, model.action_count, B), (rng.random(B) < 0.15).astype(int))
+    alphas = torch.as_tensor(np.abs(rng.standard_normal((G, model.padded_states))).astype(np.float32), device=dev)
+    for _ in range(2):
+        parallel.backup_sharded(model, bs, alphas, 0.99)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        new_alpha, best_a = parallel.backup_sharded(model, bs, alphas, 0.99)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    assert new_alpha.shape[0] == B
+    flops = 2.0 * B * model.padded_states * ((G + 15) // 16 * 16) * model.action_count * model.observation_count
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    tf32_peak = peaks.get('bf16_tflops', 1590.0) / 2.0
+    issued = 3.0 * flops / (ms * 1e-3) / 1e12 / world
+    return {'value': B / (ms * 1e-3), 'unit': 'belief-backups/s', 'belief_points': B, 'alpha_vectors': G, 'ms_per_backup': ms, 'scaling': 'strong',
+            'collective': 'all_gather of the new alpha vectors (B/N x Sp f32 + actions) per backup' if world > 1 else 'none (1 rank)',
+            'roofline': {'kernel': 'umma_ts_kernel', 'bound': 'tensor', 'achieved': issued, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': issued / tf32_peak,
+                         'note': 'issued TF32 flop (3 passes of the split-precision scheme) per GPU over the WHOLE backup time (Gamma build, GEMM, assembly, all-gather); '
+                                 'peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)'}}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -242,6 +288,10 @@ def run_ours(args) -> None:
     d2h = 22.0 * e2e_steps / max(len(hist), 1)                 # int32 action + 2 x int32 position + float64 odor + 2 flag bytes per live agent
     h2d = 16.0 * n / max(len(hist), 1)                         # start points (2 x int32) + time shifts (int64), once per run
 
+    # ---- second half of the BASELINE metric: PBVI belief-backups/s (C3: B = 10 000 belief points, sharded over the ranks,
+    #      new alpha vectors all-gathered with NCCL); reported inside the same line under "backup" ----------------------------
+    backup = measure_backup(onb, model, world, rank, dev, args) if not args.no_backup else None
+
     # ---- reduce over ranks (device time = max over ranks; work = sum) ------------------------------------
     stats = torch.tensor([elapsed_ms, e2e_ms, float(agent_steps), float(e2e_steps)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -267,10 +317,15 @@ def run_ours(args) -> None:
             'gpu_launches': launches,
             'clocks': clk,
             'roofline': {'kernel': 'belief_step_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                         'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
+                         # ncu --set full, profiles/r1f_ncu_full_raw_belief_step_and_umma_ts.csv: dram read 12.34 GB + write 12.29 GB per launch
+                         # at 99 953 updated rows = 246 442 B per updated agent (algorithmic 246 344 B): scaled to this run's launches
+                         'traffic': 246442.0 * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if bs_bytes else None,
+                         'traffic_unit': 'bytes per launch (ncu r1f capture, scaled by updated rows)', 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
                          'share_of_step': sum(bs_ms) / elapsed_ms, 'evaluate_ms_per_step': statistics.mean(ev_ms) if ev_ms else None,
                          'belief_step_ms_per_step': statistics.mean(bs_ms) if bs_ms else None},
         }
+        if backup is not None:
+            line['backup'] = backup
         if not args.no_cpu_baseline and world == 1:
             vf = agent.value_function
             r = cpu_sample(vf.alpha_vector_array, vf.actions, args.cpu_agents, args.cpu_steps)
