@@ -158,6 +158,21 @@ int olfnav_backup_assemble(const olfnav_model* m, const float* gamma_ao, int64_t
                            const int32_t* best_g, const int32_t* best_a, int64_t n_beliefs,
                            float* alpha_new, int64_t ld_new, void* stream);
 
+/* Row-pair reductions used by the belief-point selection heuristics and the pruning of solvers.*.solve
+ * (agents/pbvi_ssea_agent.py:170, agents/pbvi_ger_agent.py:170, prune_level of every train(), agents/pbvi_agent.py:584-658):
+ * out[i * ny + j] = reduce_s f(x_i(s), y_j(s)) with x_i = X[i,:] * sx[i], y_j = Y[j,:] * sy[j] (sx / sy NULL = 1), s < row_len:
+ *   OLFNAV_PAIR_L1         f = |x - y|                                         (L1 distance between beliefs: SSEA)
+ *   OLFNAV_PAIR_GER        f = (x - y) * ((x >= y ? vmax : vmin) - W[j,s])     (Pineau's error bound of belief x_i w.r.t. belief y_j
+ *                                                                               whose best alpha vector is W[j,:]: GER)
+ *   OLFNAV_PAIR_DOMINATED  out = 1 if y_j >= x_i everywhere and > somewhere, else 0   (point-wise dominance pruning of alpha vectors) */
+#define OLFNAV_PAIR_L1 0
+#define OLFNAV_PAIR_GER 1
+#define OLFNAV_PAIR_DOMINATED 2
+int olfnav_pair_reduce(int mode, const float* X, int64_t ldx, const float* sx, int64_t nx,
+                       const float* Y, int64_t ldy, const float* sy, int64_t ny,
+                       const float* W, int64_t ldw, float vmax, float vmin, int64_t row_len,
+                       float* out /* [dev] nx x ny */, void* stream);
+
 /* solvers.VI.solve sweep      agents/qmdp_agent.py:145-153
  * Q_out[a][s] = r_a(s) + discount * max_a' Q_in[a'][R_a(s)] ; max_change = max_s |V_out - V_in|.
  * float64 on purpose: V grows to 1/(1-discount) while the stopping rule looks at changes of 1e-4. */

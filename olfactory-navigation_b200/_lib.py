@@ -78,6 +78,7 @@ class SimStepArgs(ctypes.Structure):
     ]
 
 
+SIGNATURES['olfnav_pair_reduce'] = (_i, [_i, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, ctypes.c_float, ctypes.c_float, _i64, _p, _p])
 SIGNATURES['olfnav_sim_step'] = (_i, [_p, _p, _p, ctypes.POINTER(SimStepArgs), _p])
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -82,4 +82,5 @@ class HSVI_Agent(PBVI_Agent):
 
     def train(self, expansions: int = 10, **kwargs):
         common, flavour = _split(dict(kwargs, expansions=expansions), ('mdp_policy', 'vi_horizon', 'epsilon'))
+        flavour['return_mdp_policy'] = True           # reference agents/hsvi_agent.py:184: value_function, hist, mdp_policy = HSVI.solve(...)
         return self._train_with(solvers.HSVI, flavour, **common)

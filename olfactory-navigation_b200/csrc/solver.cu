@@ -248,3 +248,67 @@ extern "C" int olfnav_backup_assemble(const olfnav_model* m, const float* gamma_
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// Row-pair reductions (see olfnav_pair_reduce in the header).  One CTA per (x_i, y_j) pair; both rows stream from L2 / HBM.
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_reduce_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ sx,
+                                                          const float* __restrict__ Y, long long ldy, const float* __restrict__ sy, int ny,
+                                                          const float* __restrict__ Wt, long long ldw, float vmax, float vmin, int len4,
+                                                          float* __restrict__ out) {
+    __shared__ float red[33];
+    const long long i = blockIdx.y, j = blockIdx.x;
+    const float a = sx ? sx[i] : 1.f, b = sy ? sy[j] : 1.f;
+    const float4* x4 = reinterpret_cast<const float4*>(X + i * ldx);
+    const float4* y4 = reinterpret_cast<const float4*>(Y + j * ldy);
+    const float4* w4 = MODE == OLFNAV_PAIR_GER ? reinterpret_cast<const float4*>(Wt + j * ldw) : nullptr;
+    float acc = 0.f, acc2 = 0.f;
+    for (int c = threadIdx.x; c < len4; c += 256) {
+        const float4 xv = x4[c], yv = y4[c];
+        const float xs[4] = {xv.x * a, xv.y * a, xv.z * a, xv.w * a};
+        const float ys[4] = {yv.x * b, yv.y * b, yv.z * b, yv.w * b};
+        if (MODE == OLFNAV_PAIR_L1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc += fabsf(xs[e] - ys[e]);
+        } else if (MODE == OLFNAV_PAIR_GER) {
+            const float4 wv = w4[c];
+            const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = xs[e] - ys[e];
+                acc += d * ((d >= 0.f ? vmax : vmin) - ws[e]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { acc += (ys[e] < xs[e]) ? 1.f : 0.f; acc2 += (ys[e] > xs[e]) ? 1.f : 0.f; }
+        }
+    }
+    const float t = block_sum<256>(acc, red);
+    if (MODE == OLFNAV_PAIR_DOMINATED) {
+        const float t2 = block_sum<256>(acc2, red);
+        if (threadIdx.x == 0) out[i * ny + j] = (t == 0.f && t2 > 0.f) ? 1.f : 0.f;
+    } else if (threadIdx.x == 0) {
+        out[i * ny + j] = t;
+    }
+}
+}  // namespace
+
+extern "C" int olfnav_pair_reduce(int mode, const float* X, int64_t ldx, const float* sx, int64_t nx, const float* Y, int64_t ldy,
+                                  const float* sy, int64_t ny, const float* W, int64_t ldw, float vmax, float vmin, int64_t row_len,
+                                  float* out, void* stream) {
+    OLF_REQUIRE(X && Y && out, "pair_reduce: null argument");
+    OLF_REQUIRE(mode >= 0 && mode <= 2 && (mode != OLFNAV_PAIR_GER || W), "pair_reduce: bad mode or missing W");
+    OLF_REQUIRE((row_len % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0 && (ldw % 4) == 0, "pair_reduce: rows must be float4 aligned");
+    OLF_REQUIRE(nx >= 0 && ny >= 0 && nx <= 65535 && ny <= 0x7fffffffLL, "pair_reduce: nx <= 65535 rows per call");
+    if (nx == 0 || ny == 0) return OLFNAV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ny, (unsigned)nx);
+    const int len4 = (int)(row_len / 4);
+    if (mode == OLFNAV_PAIR_L1)       pair_reduce_kernel<OLFNAV_PAIR_L1><<<grid, 256, 0, st>>>(X, ldx, sx, Y, ldy, sy, (int)ny, W, ldw, vmax, vmin, len4, out);
+    else if (mode == OLFNAV_PAIR_GER) pair_reduce_kernel<OLFNAV_PAIR_GER><<<grid, 256, 0, st>>>(X, ldx, sx, Y, ldy, sy, (int)ny, W, ldw, vmax, vmin, len4, out);
+    else                              pair_reduce_kernel<OLFNAV_PAIR_DOMINATED><<<grid, 256, 0, st>>>(X, ldx, sx, Y, ldy, sy, (int)ny, W, ldw, vmax, vmin, len4, out);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}

@@ -4,7 +4,7 @@ Device solvers — the `pomdp_toolkit.solvers` surface the reference's agents ca
   FSVI.solve               reference agents/fsvi_agent.py:201-224
   PBVI_RA/SSRA/SSGA/SSEA   reference agents/pbvi_ra_agent.py:168, pbvi_ssra_agent.py:170,
                            pbvi_ssga_agent.py:176-198, pbvi_ssea_agent.py:170
-  PBVI_GER/Perseus/HSVI    expand heuristics are SURVEY §8 f2 ("next"): NotImplementedError.
+  PBVI_GER/Perseus/HSVI    reference agents/pbvi_ger_agent.py:170, perseus_agent.py:176-196, hsvi_agent.py:184-208
 
 The backup runs on the device in three steps through the C ABI:
   olfnav_backup_gamma    Gamma_{a,o}^g = gamma * O_o(R_a(.)) * alpha_g(R_a(.))          streaming kernel
@@ -229,7 +229,7 @@ class _PBVI:
             pruned = 0
             if prune_interval > 0 and (backup_count % prune_interval) == 0 and prune_level >= 1:
                 before = alphas.shape[0]
-                alphas, actions = _unique_rows(alphas, actions)
+                alphas, actions = prune_alphas(alphas, actions, prune_level)
                 pruned = before - alphas.shape[0]
             if 0 < limit_value_function_size < alphas.shape[0]:
                 G = alphas.shape[0]
@@ -379,23 +379,286 @@ class PBVI_RA(_PBVI):
         return BeliefSet(model, pts / np.sum(pts, axis=1, keepdims=True))
 
 
-class _Next(_PBVI):
-    @classmethod
-    def solve(cls, *args, **kwargs):
-        raise NotImplementedError(f'{cls.name}: expand heuristic not built yet (SURVEY §8 f2, "next"); it shares the device backup.')
+def _pair_reduce(mode: int, X: torch.Tensor, sx, Y: torch.Tensor, sy, W: torch.Tensor = None, vmax: float = 0.0, vmin: float = 0.0,
+                 row_len: int = None) -> torch.Tensor:
+    'out[i, j] = reduce_s f(X[i]*sx[i], Y[j]*sy[j])  (olfnav_pair_reduce: 0 = L1 distance, 1 = GER error term, 2 = dominated flag).'
+    nx, ny = X.shape[0], Y.shape[0]
+    out = torch.empty((nx, ny), dtype=torch.float32, device=X.device)
+    row_len = X.shape[1] if row_len is None else row_len
+    for i0 in range(0, nx, 65535):
+        i1 = min(nx, i0 + 65535)
+        check(lib.olfnav_pair_reduce(mode, ptr(X[i0:i1]), X.stride(0), None if sx is None else ptr(sx[i0:i1]), i1 - i0,
+                                     ptr(Y), Y.stride(0), None if sy is None else ptr(sy), ny,
+                                     None if W is None else ptr(W), 0 if W is None else W.stride(0), vmax, vmin, row_len,
+                                     ptr(out[i0:i1]), stream()))
+    return out
 
 
-class PBVI_SSEA(_Next):
+def _batched_updates(model: POMDP, bs: BeliefSet, rows, acts, obss):
+    '''
+    One belief-step launch producing b_{a,o} for every (source row, action, observation) triple.
+    Returns (BeliefSet of len(rows) rows, ok (bool tensor), p = P(o | b, a) (float32 tensor, 0 where impossible)).
+    '''
+    dev = bs._b.device
+    n = len(rows)
+    Sp = model.padded_states
+    r = torch.as_tensor(np.asarray(rows), dtype=torch.int32, device=dev).contiguous()
+    a = torch.as_tensor(np.asarray(acts), dtype=torch.int32, device=dev).contiguous()
+    o = torch.as_tensor(np.asarray(obss), dtype=torch.int32, device=dev).contiguous()
+    out_b = torch.empty((max(n, 1), Sp), dtype=torch.float32, device=dev)
+    out_s = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    ok = torch.zeros(max(n, 1), dtype=torch.uint8, device=dev)
+    if n:
+        with torch.cuda.device(bs.device):
+            check(lib.olfnav_belief_step(model.handle(bs.device), ptr(bs._b), ptr(out_b), Sp, n, ptr(a), ptr(o), ptr(r), None,
+                                         ptr(bs._scale), ptr(out_s), ptr(ok), stream()))
+    okb = ok[:n].bool()
+    p = torch.where(okb, 1.0 / out_s[:n].clamp_min(1e-38), torch.zeros_like(out_s[:n]))
+    return BeliefSet(model, _buffers=(out_b, out_s, n), device=bs.device), okb, p
+
+
+def _take_rows(model: POMDP, bs: BeliefSet, rows) -> BeliefSet:
+    idx = torch.as_tensor(np.asarray(rows, dtype=np.int64), device=bs._b.device)
+    return BeliefSet(model, _buffers=(bs._b[idx].contiguous() if len(idx) else bs._b[:1].clone(),
+                                      bs._scale[idx].contiguous() if len(idx) else bs._scale[:1].clone(), len(idx)), device=bs.device)
+
+
+def prune_alphas(alphas: torch.Tensor, actions: torch.Tensor, level: int):
+    '''
+    ValueFunction pruning (prune_level of every train(), reference agents/pbvi_agent.py:584-658): level >= 1 drops exact
+    duplicates, level >= 2 also vectors point-wise dominated by another single vector (olfnav_pair_reduce, DOMINATED).
+    '''
+    if level >= 1:
+        alphas, actions = _unique_rows(alphas, actions)
+    if level >= 2 and alphas.shape[0] > 1:
+        a = alphas.contiguous()
+        dom = _pair_reduce(2, a, None, a, None)                    # dom[i, j] = 1 if alpha_j dominates alpha_i
+        keep = dom.sum(dim=1) == 0
+        alphas, actions = a[keep], actions[keep]
+    return alphas, actions
+
+
+class PBVI_SSEA(_PBVI):
+    '''
+    Stochastic Simulation with Exploratory Action (agents/pbvi_ssea_agent.py:170): for each of the first `max_generation`
+    beliefs simulate one step per action and keep the successor farthest (L1) from the current set (which grows as successors
+    are picked).  All candidates come from ONE batched belief-step launch and the distances from two olfnav_pair_reduce
+    launches (candidates x set, candidates x candidates); the sequential pick is host bookkeeping on those matrices.
+    Draws per belief, per action: rng.random() for the state, rng.random() for the observation (same order as the oracle).
+    '''
     name = 'PBVI_SSEA'
 
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, **kw) -> BeliefSet:
+        m, A = min(max_generation, len(belief_set)), model.action_count
+        dense = belief_set.belief_tensor(torch.float64)[:m].cpu().numpy()
+        rows, acts, obss = [], [], []
+        for k in range(m):
+            cdf = np.cumsum(dense[k])
+            for a in range(A):
+                s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
+                s_p = model.transition(s, a)
+                obss.append(model.observe(s_p, a, rng.random()))
+                rows.append(k)
+                acts.append(a)
+        cand, ok, _ = _batched_updates(model, belief_set, rows, acts, obss)
+        if not bool(ok.all()):
+            raise ValueError('Impossible belief update during expand')
+        Sp = model.padded_states
+        n = len(belief_set)
+        d_set = _pair_reduce(0, cand._b, cand._scale, belief_set._b[:n], belief_set._scale[:n], row_len=Sp).min(dim=1).values.cpu().numpy()
+        d_cc = _pair_reduce(0, cand._b, cand._scale, cand._b[:len(cand)], cand._scale[:len(cand)], row_len=Sp).cpu().numpy()
+        chosen = []
+        for k in range(m):
+            best, best_d = -1, -1.0
+            for a in range(A):
+                c = k * A + a
+                d = float(min([d_set[c]] + [d_cc[c, j] for j in chosen]))
+                if d > best_d:
+                    best, best_d = c, d
+            chosen.append(best)
+        return _take_rows(model, cand, chosen)
 
-class PBVI_GER(_Next):
+
+class PBVI_GER(_PBVI):
+    '''
+    Greedy Error Reduction (agents/pbvi_ger_agent.py:10,170; Pineau et al. 2006): see the oracle's PBVI_GER for the definition.
+    All A*O successors of every belief come from one batched belief-step launch; the error bound of every successor against
+    every belief of the set is one olfnav_pair_reduce launch (GER mode) followed by a row minimum.  Deterministic.
+    '''
     name = 'PBVI_GER'
 
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, **kw) -> dict:
+        return {'gamma': gamma}
 
-class Perseus(_Next):
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, gamma=0.99, **kw) -> BeliefSet:
+        n, A, O, Sp = len(belief_set), model.action_count, model.observation_count, model.padded_states
+        vf = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas)
+        _, g_star, _ = vf.evaluate_device(belief_set)
+        alpha_b = alphas[g_star.long()].contiguous()
+        r = model.expected_rewards_table
+        vmax, vmin = float(np.max(r)) / (1.0 - gamma), float(np.min(r)) / (1.0 - gamma)
+        rows = np.repeat(np.arange(n), A * O)
+        acts = np.tile(np.repeat(np.arange(A), O), n)
+        obss = np.tile(np.arange(O), n * A)
+        succ, ok, p = _batched_updates(model, belief_set, rows, acts, obss)
+        e = _pair_reduce(1, succ._b, succ._scale, belief_set._b[:n], belief_set._scale[:n], W=alpha_b, vmax=vmax, vmin=vmin, row_len=Sp)
+        eps_bao = torch.where(ok, e.min(dim=1).values, torch.zeros_like(p)).double().view(n, A, O)
+        contrib = (p.double().view(n, A, O) * eps_bao).cpu().numpy()
+        p_h = p.view(n, A, O).cpu().numpy()
+        err = contrib.sum(axis=2)
+        a_star = np.argmax(err, axis=1)
+        score = err[np.arange(n), a_star]
+        o_star = np.argmax(contrib[np.arange(n), a_star, :], axis=1)
+        order = np.argsort(-score, kind='stable')[:max_generation]
+        pick = [int(i * A * O + a_star[i] * O + o_star[i]) for i in order if p_h[i, a_star[i], o_star[i]] > 0]
+        return _take_rows(model, succ, pick)
+
+
+class Perseus(_PBVI):
+    '''
+    Perseus (agents/perseus_agent.py:99,176-196; Spaan & Vlassis 2005): see the oracle's Perseus for the definition.
+    The stage backs up ALL beliefs against the stage's starting value function in one batched device backup (every per-belief
+    backup of the sequential algorithm uses that same value function, so they are independent), takes the cross values
+    candidate_i . b_j from one FP32 matrix product, and replays the randomised improve-only selection on the host.
+    '''
     name = 'Perseus'
 
+    @classmethod
+    def walk(cls, model, belief_set, alphas, actions, max_generation, rng, use_policy) -> BeliefSet:
+        n = len(belief_set)
+        b0 = belief_set.belief_tensor(torch.float64)[n - 1].cpu().numpy()
+        cdf = np.cumsum(b0)
+        s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
+        cur = _take_rows(model, belief_set, [n - 1])
+        vf = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas) if use_policy else None
+        out = None
+        for _ in range(max_generation):
+            if use_policy:
+                a = int(vf.evaluate_device(cur)[2][0])
+            else:
+                a = min(int(rng.random() * model.action_count), model.action_count - 1)
+            s_p = model.transition(s, a)
+            o = model.observe(s_p, a, rng.random())
+            cur = _chain_updates(model, cur, 0, [(a, o)])
+            out = cur if out is None else out.union(cur)
+            s = s_p
+            if model.end_mask[s]:
+                break
+        return out if out is not None else BeliefSet(model, np.zeros((0, model.state_count)))
 
-class HSVI(_Next):
+    @classmethod
+    def stage(cls, model, belief_set, alphas, actions, gamma, rng, gemm_path=0):
+        n = len(belief_set)
+        vf = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas)
+        v_old, g_old, _ = vf.evaluate_device(belief_set, gemm_path)
+        new_alpha, best_a, new_v, _ = backup_device(model, belief_set, alphas, gamma, gemm_path)
+        improved = new_v >= v_old
+        cand = torch.where(improved[:, None], new_alpha, alphas[g_old.long()])
+        cand_a = torch.where(improved, best_a, actions[g_old.long()])
+        cross = (cand @ belief_set._b[:n].T) * belief_set._scale[:n][None, :]          # cross[i, j] = cand_i . b_j   (FP32)
+        cross_h, v_old_h = cross.double().cpu().numpy(), v_old.double().cpu().numpy()
+        todo = np.arange(n)
+        kept = []
+        v_new = np.full(n, -np.inf)
+        while len(todo):
+            i = int(todo[min(int(rng.random() * len(todo)), len(todo) - 1)])
+            kept.append(i)
+            v_new = np.maximum(v_new, cross_h[i])
+            v_new[i] = max(v_new[i], v_old_h[i])            # the kept vector is at least as good as the old one at its own belief
+            todo = todo[v_new[todo] < v_old_h[todo]]
+        idx = torch.as_tensor(kept, dtype=torch.long, device=alphas.device)
+        return cand[idx].contiguous(), cand_a[idx].contiguous()
+
+    @classmethod
+    def solve(cls, model, expansions=10, update_passes=1, max_belief_growth=10, initial_belief=None, initial_value_function=None,
+              prune_level=1, prune_interval=10, limit_value_function_size=-1, gamma=0.99, eps=1e-6, convergence_stop=False,
+              use_gpu=True, use_reachability=True, rng=None, history_tracking_level=1, print_progress=True, print_stats=True,
+              use_policy_to_choose_actions=False, gemm_path=0, **kw):
+        rng = np.random.default_rng() if rng is None else rng
+        device = current_device()
+        dev = torch.device('cuda', device)
+        hist = SolverHistory(model, history_tracking_level, gamma, eps, cls.name)
+        t_start = time.perf_counter()
+        if initial_belief is None:
+            belief_set = BeliefSet(model, 1)
+        elif isinstance(initial_belief, Belief):
+            belief_set = BeliefSet(model, initial_belief.values[None, :])
+        else:
+            belief_set = initial_belief
+        vf0 = ValueFunction(model, model.expected_rewards_table.T.copy(), model.actions) if initial_value_function is None else initial_value_function
+        alphas = vf0.device_alphas(device).clone()
+        actions = torch.as_tensor(vf0.actions, dtype=torch.int32, device=dev)
+
+        def values_of(bs, al, ac):
+            return ValueFunction(model, action_list=ac.cpu().numpy(), _device_alphas=al).evaluate_device(bs, gemm_path)[0]
+        old_values = values_of(belief_set, alphas, actions)
+        backup_count = 0
+        for _ in range(expansions):
+            t0 = time.perf_counter()
+            belief_set = belief_set.union(cls.walk(model, belief_set, alphas, actions, max_belief_growth, rng, bool(use_policy_to_choose_actions)))
+            torch.cuda.synchronize(dev)
+            hist.expansion_times.append(time.perf_counter() - t0)
+            hist.beliefs_counts.append(len(belief_set))
+            t0 = time.perf_counter()
+            for _ in range(update_passes):
+                alphas, actions = cls.stage(model, belief_set, alphas, actions, gamma, rng, gemm_path)
+                backup_count += 1
+            torch.cuda.synchronize(dev)
+            hist.backup_times.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            before = alphas.shape[0]
+            if prune_interval > 0 and backup_count % prune_interval == 0:
+                alphas, actions = prune_alphas(alphas, actions, prune_level)
+            hist.pruning_times.append(time.perf_counter() - t0)
+            hist.prune_counts.append(before - alphas.shape[0])
+            hist.alpha_vector_counts.append(int(alphas.shape[0]))
+            new_values = values_of(belief_set, alphas, actions)
+            change = float((new_values[:len(old_values)] - old_values).abs().max()) if len(old_values) else float('inf')
+            old_values = new_values
+            hist.value_function_changes.append(change)
+            if convergence_stop and change < eps:
+                break
+        value_function = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas.contiguous())
+        hist.total_time = time.perf_counter() - t_start
+        hist.final_belief_set = belief_set
+        return value_function, hist
+
+
+class HSVI(_PBVI):
+    '''
+    Heuristic Search Value Iteration (agents/hsvi_agent.py:100-102,184-208; Smith & Simmons 2004): see the oracle's HSVI for
+    the definition (upper bound = the MDP policy's Q rows, lower bound = the alpha vectors, one deterministic descent per
+    expansion).  Per depth: the O successors of the current belief under a* are one batched belief-step launch, both bounds
+    are evaluated on them with the device evaluate.
+    '''
     name = 'HSVI'
+    full_backup = False
+    dominance_prune = True
+
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, mdp_policy=None, vi_horizon=1000, epsilon=0.99, use_reachability=True, **kw):
+        if mdp_policy is None:
+            mdp_policy, _ = VI.solve(model, horizon=vi_horizon, gamma=gamma, eps=eps, print_progress=print_progress)
+        return {'mdp_policy': mdp_policy, 'epsilon': float(epsilon), 'gamma': gamma}
+
+    @classmethod
+    def expand(cls, model, belief_set, alphas, actions, max_generation, rng, mdp_policy=None, epsilon=0.99, gamma=0.99, **kw) -> BeliefSet:
+        O = model.observation_count
+        lower = ValueFunction(model, action_list=actions.cpu().numpy(), _device_alphas=alphas)
+        cur = _take_rows(model, belief_set, [0])
+        out = None
+        for depth in range(max_generation):
+            a = int(mdp_policy.evaluate_device(cur)[2][0])                         # first argmax_a b.Q_a
+            succ, ok, p = _batched_updates(model, cur, [0] * O, [a] * O, list(range(O)))
+            up = mdp_policy.evaluate_device(succ)[0].double()
+            lo = lower.evaluate_device(succ)[0].double()
+            excess = torch.where(ok, p.double() * ((up - lo) - epsilon * gamma ** (-(depth + 1))), torch.full_like(up, -np.inf)).cpu().numpy()
+            o = int(np.argmax(excess))
+            if not (excess[o] > 0):
+                break
+            cur = _take_rows(model, succ, [o])
+            out = cur if out is None else out.union(cur)
+        return out if out is not None else BeliefSet(model, np.zeros((0, model.state_count)))

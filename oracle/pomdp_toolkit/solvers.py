@@ -431,19 +431,199 @@ class PBVI_RA(_PBVI):
         return BeliefSet(model, pts / np.sum(pts, axis=1, keepdims=True))
 
 
-class _Next(_PBVI):
-    @classmethod
-    def solve(cls, *args, **kwargs):
-        raise NotImplementedError(f'{cls.name}: expand heuristic not restated yet (SURVEY §8 f2, "next"); it shares backup() above.')
-
-
-class PBVI_GER(_Next):
+class PBVI_GER(_PBVI):
+    '''
+    Greedy Error Reduction (Pineau, Gordon & Thrun 2006, the PBVI variant the reference cites at agents/pbvi_agent.py:239
+    and describes at agents/pbvi_ger_agent.py:10: "choosing belief points that will most decrease the error in the value
+    function").  For a candidate successor b' the error bound is
+        eps(b') = min_{b in B} sum_s (b'(s) - b(s)) * ( (Vmax - alpha_b(s)) if b'(s) >= b(s) else (Vmin - alpha_b(s)) ),
+    alpha_b = the best vector at b, Vmax = max r / (1 - gamma), Vmin = min r / (1 - gamma).
+    Per belief b:  err(b, a) = sum_o P(o|b,a) eps(b_{a,o});  a* = first argmax_a;  o* = first argmax_o P(o|b,a*) eps(b_{a*,o});
+    the `max_generation` beliefs with the largest err(b, a*) (stable order) contribute their b_{a*,o*}.  Deterministic.
+    '''
     name = 'PBVI_GER'
 
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, **kw) -> dict:
+        return {'gamma': gamma}
 
-class Perseus(_Next):
+    @classmethod
+    def expand(cls, model, belief_set, value_function, max_generation, rng, gamma=0.99, **kw) -> BeliefSet:
+        B = belief_set.belief_array
+        n = len(B)
+        av = value_function.alpha_vector_array
+        alpha_b = av[np.argmax(B @ av.T, axis=1)]                      # (n, S)
+        r = model.expected_rewards_table
+        vmax, vmin = float(np.max(r)) / (1.0 - gamma), float(np.min(r)) / (1.0 - gamma)
+        u, p = belief_set.unnormalised_successors()                    # (n, A, O, S), (n, A, O)
+        A, O = model.action_count, model.observation_count
+        eps_bao = np.zeros((n, A, O))
+        for i in range(n):
+            for a in range(A):
+                for o in range(O):
+                    if p[i, a, o] <= 0:
+                        continue
+                    bp = u[i, a, o] / p[i, a, o]
+                    d = bp[None, :] - B                                # (n, S)
+                    w = np.where(d >= 0, vmax - alpha_b, vmin - alpha_b)
+                    eps_bao[i, a, o] = float(np.min(np.sum(d * w, axis=1)))
+        contrib = p * eps_bao                                          # (n, A, O)
+        err = np.sum(contrib, axis=2)                                  # (n, A)
+        a_star = np.argmax(err, axis=1)
+        score = err[np.arange(n), a_star]
+        o_star = np.argmax(contrib[np.arange(n), a_star, :], axis=1)
+        order = np.argsort(-score, kind='stable')[:max_generation]
+        out = [u[i, a_star[i], o_star[i]] / p[i, a_star[i], o_star[i]] for i in order if p[i, a_star[i], o_star[i]] > 0]
+        return BeliefSet(model, np.array(out).reshape(-1, model.state_count))
+
+
+class Perseus(_PBVI):
+    '''
+    Perseus (Spaan & Vlassis 2005; reference agents/perseus_agent.py:99,176-196).
+    Expand: a random walk of `max_generation` steps continuing from the LAST belief of the set (the initial belief the first
+    time): s ~ b once, then per step a = uniform random action (or the value function's greedy action at the current belief when
+    `use_policy_to_choose_actions`), s' = T(s, a), o ~ O(.|s', a), b <- update(b, a, o); stops early in an end state.
+    Draws: rng.random() for s, then per step [rng.random() for a when random] and rng.random() for o.
+    Backup: one randomised improve-only stage over the WHOLE belief set with the value function V of the stage's start:
+        todo = all beliefs; repeat: i = todo[min(int(rng.random() * len(todo)), len(todo) - 1)];
+        alpha = backup(b_i, V); keep alpha if alpha.b_i >= V(b_i) else the best old vector at b_i;
+        drop from todo every belief whose value under the vectors kept so far is >= its value under V.
+    The kept vectors replace the value function.
+    '''
     name = 'Perseus'
 
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, use_policy_to_choose_actions=False, **kw) -> dict:
+        return {'use_policy': bool(use_policy_to_choose_actions)}
 
-class HSVI(_Next):
+    @classmethod
+    def expand(cls, model, belief_set, value_function, max_generation, rng, use_policy=False, **kw) -> BeliefSet:
+        b = Belief(model, belief_set.belief_array[-1])
+        s = b.random_state(rng.random())
+        out = []
+        for _ in range(max_generation):
+            if use_policy:
+                a = int(value_function.actions[np.argmax(value_function.alpha_vector_array @ b.values)])
+            else:
+                a = min(int(rng.random() * model.action_count), model.action_count - 1)
+            s_p = model.transition(s, a, 0.0)
+            o = model.observe(s_p, a, rng.random())
+            b = b.update(a, o)
+            out.append(b)
+            s = s_p
+            if model.end_mask[s]:
+                break
+        return BeliefSet(model, out)
+
+    @classmethod
+    def stage(cls, model, belief_set, value_function, gamma, rng) -> ValueFunction:
+        B = belief_set.belief_array
+        av, ac = value_function.alpha_vector_array, value_function.actions
+        scores = B @ av.T
+        v_old, g_old = np.max(scores, axis=1), np.argmax(scores, axis=1)
+        todo = np.arange(len(B))
+        kept_v, kept_a = [], []
+        v_new = np.full(len(B), -np.inf)
+        while len(todo):
+            i = int(todo[min(int(rng.random() * len(todo)), len(todo) - 1)])
+            _, det = backup(model, BeliefSet(model, B[i:i + 1]), value_function, gamma, belief_dominance_prune=False, return_details=True)
+            if det['new_value'][0] >= v_old[i]:
+                vec, act = det['new_alpha'][0], int(det['best_a'][0])
+            else:
+                vec, act = av[g_old[i]], int(ac[g_old[i]])
+            kept_v.append(vec)
+            kept_a.append(act)
+            v_new = np.maximum(v_new, B @ vec)
+            todo = todo[v_new[todo] < v_old[todo]]
+        return ValueFunction(model, np.array(kept_v), np.array(kept_a))
+
+    @classmethod
+    def solve(cls, model, expansions=10, update_passes=1, max_belief_growth=10, initial_belief=None, initial_value_function=None,
+              prune_level=1, prune_interval=10, limit_value_function_size=-1, gamma=0.99, eps=1e-6, convergence_stop=False,
+              use_gpu=False, use_reachability=True, rng=None, history_tracking_level=1, print_progress=True, print_stats=True,
+              use_policy_to_choose_actions=False, **kw):
+        rng = np.random.default_rng() if rng is None else rng
+        hist = SolverHistory(model, history_tracking_level, gamma, eps, cls.name)
+        t_start = time.perf_counter()
+        if initial_belief is None:
+            belief_set = BeliefSet(model, [Belief(model)])
+        elif isinstance(initial_belief, Belief):
+            belief_set = BeliefSet(model, [initial_belief])
+        else:
+            belief_set = initial_belief
+        if initial_value_function is None:
+            value_function = ValueFunction(model, model.expected_rewards_table.T.copy(), model.actions)
+        else:
+            value_function = ValueFunction(model, initial_value_function.alpha_vector_array.copy(), initial_value_function.actions.copy())
+        old_values = np.max(belief_set.belief_array @ value_function.alpha_vector_array.T, axis=1)
+        backup_count = 0
+        for _ in range(expansions):
+            t0 = time.perf_counter()
+            belief_set = belief_set.union(cls.expand(model, belief_set, value_function, max_belief_growth, rng, use_policy=use_policy_to_choose_actions))
+            hist.expansion_times.append(time.perf_counter() - t0)
+            hist.beliefs_counts.append(len(belief_set))
+            t0 = time.perf_counter()
+            for _ in range(update_passes):
+                value_function = cls.stage(model, belief_set, value_function, gamma, rng)
+                backup_count += 1
+            hist.backup_times.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            pruned = value_function.prune(prune_level) if (prune_interval > 0 and backup_count % prune_interval == 0) else 0
+            hist.pruning_times.append(time.perf_counter() - t0)
+            hist.prune_counts.append(pruned)
+            hist.alpha_vector_counts.append(len(value_function))
+            new_values = np.max(belief_set.belief_array @ value_function.alpha_vector_array.T, axis=1)
+            change = float(np.max(np.abs(new_values[:len(old_values)] - old_values))) if len(old_values) else np.inf
+            old_values = new_values
+            hist.value_function_changes.append(change)
+            if convergence_stop and change < eps:
+                break
+        hist.total_time = time.perf_counter() - t_start
+        hist.final_belief_set = belief_set
+        return value_function, hist
+
+
+class HSVI(_PBVI):
+    '''
+    Heuristic Search Value Iteration (Smith & Simmons 2004; reference agents/hsvi_agent.py:100-102,184-208: parameters
+    `mdp_policy`, `vi_horizon`, `epsilon`, and "backup only on the beliefs generated by the expand function").
+    Lower bound = the alpha vectors, upper bound = the MDP policy (Q_MDP): Vup(b) = max_a b.Q_a.
+    Expand: one deterministic descent of at most `max_generation` steps from the initial belief (row 0):
+        a* = first argmax_a b.Q_a;   for every o with P(o|b,a*) > 0:  gap_o = Vup(b_o) - Vlow(b_o);
+        excess_o = P(o|b,a*) * (gap_o - epsilon * gamma^-(depth+1));   o* = first argmax_o excess_o;
+        stop when excess_{o*} <= 0, else b <- b_{a*,o*} and collect it.
+    Backup on the new beliefs only, appended, kept only where they improve (like FSVI).
+    '''
     name = 'HSVI'
+    full_backup = False
+    dominance_prune = True
+
+    @classmethod
+    def prepare(cls, model, gamma, eps, print_progress, mdp_policy=None, vi_horizon=1000, epsilon=0.99, use_reachability=True, **kw):
+        if mdp_policy is None:
+            mdp_policy, _ = VI.solve(model, horizon=vi_horizon, gamma=gamma, eps=eps, print_progress=print_progress)
+        return {'mdp_policy': mdp_policy, 'epsilon': float(epsilon), 'gamma': gamma}
+
+    @classmethod
+    def expand(cls, model, belief_set, value_function, max_generation, rng, mdp_policy=None, epsilon=0.99, gamma=0.99, **kw) -> BeliefSet:
+        Q = mdp_policy.alpha_vector_array                                 # (A, S)
+        av = value_function.alpha_vector_array
+        b = belief_set.belief_array[0]
+        out = []
+        for depth in range(max_generation):
+            a = int(np.argmax(Q @ b))
+            u, p = BeliefSet(model, b[None, :]).unnormalised_successors()
+            u, p = u[0, a], p[0, a]                                       # (O, S), (O,)
+            excess = np.full(model.observation_count, -np.inf)
+            for o in range(model.observation_count):
+                if p[o] <= 0:
+                    continue
+                bo = u[o] / p[o]
+                gap = float(np.max(Q @ bo)) - float(np.max(av @ bo))
+                excess[o] = p[o] * (gap - epsilon * gamma ** (-(depth + 1)))
+            o = int(np.argmax(excess))
+            if not (excess[o] > 0):
+                break
+            b = u[o] / p[o]
+            out.append(b)
+        return BeliefSet(model, np.array(out).reshape(-1, model.state_count))

@@ -114,3 +114,21 @@ def test_oracle_sim_loop_reproduces_reference_run_test(cfg, label, tk):
     sims, act, pos, odor = out['records'][0]
     assert np.array_equal(pos, g['positions'][0][sims]) and np.array_equal(setup['action_set'][act], g['actions'][0][sims])
     assert np.array_equal(odor.astype(np.float32), g['observations'][0][sims])
+
+
+def test_oracle_next_solvers_run_and_improve():
+    'SSEA / GER / Perseus / HSVI restatements: deterministic under a seed, belief sets grow, value functions stay valid lower bounds.'
+    from conftest import make, oracle_model
+    import pomdp_toolkit as tk
+    _, agent = make('T0')
+    om = oracle_model(agent.model)
+    q, _ = tk.solvers.VI.solve(om, horizon=1000, gamma=0.99, eps=1e-6, print_progress=False)
+    upper = q.alpha_vector_array                      # Q_MDP is an upper bound of the POMDP value
+    for name, kw in [('PBVI_SSEA', {}), ('PBVI_GER', {}), ('Perseus', {}), ('HSVI', {'epsilon': 0.05})]:
+        runs = [getattr(tk.solvers, name).solve(om, expansions=3, max_belief_growth=4, rng=np.random.default_rng(2), print_progress=False, **kw) for _ in range(2)]
+        a0, a1 = runs[0][0].alpha_vector_array, runs[1][0].alpha_vector_array
+        assert a0.shape == a1.shape and np.array_equal(a0, a1), name
+        hist = runs[0][1]
+        assert hist.beliefs_counts == sorted(hist.beliefs_counts) and hist.beliefs_counts[-1] > 1
+        B = hist.final_belief_set.belief_array
+        assert np.all(np.max(B @ a0.T, axis=1) <= np.max(B @ upper.T, axis=1) + 1e-9), name
