@@ -226,8 +226,6 @@ class PBVI_Agent(BeliefSimulationMixin, Agent):
     # -- persistence (pbvi_agent.py:450-581; load fixed) --------------------------------
     def save(self, folder: str = None, force: bool = False, save_environment: bool = False) -> None:
         assert self.trained_at is not None, 'The agent is not trained, there is nothing to save.'
-        if save_environment:
-            raise NotImplementedError('Environment.save is out of scope (SURVEY §8 f3)')
         folder = f'./Agent-{self.name}' if folder is None else folder + '/Agent-' + self.name
         if not os.path.exists(folder):
             os.mkdir(folder)
@@ -244,6 +242,8 @@ class PBVI_Agent(BeliefSimulationMixin, Agent):
         with open(folder + '/METADATA.json', 'w') as f:
             json.dump(meta, f, indent=4)
         self.value_function.save(folder=folder, file_name='Value_Function.npy')
+        if save_environment:
+            self.environment.save(folder=folder, save_arrays=self.environment.data_file_path is None, force=force)
         self.saved_at = os.path.abspath(folder).replace('\\', '/')
         print(f'Agent saved to: {folder}')
 
@@ -252,7 +252,12 @@ class PBVI_Agent(BeliefSimulationMixin, Agent):
         with open(folder + '/METADATA.json', 'r') as f:
             meta = json.load(f)
         if environment is None:
-            raise NotImplementedError('Environment.load is out of scope (SURVEY §8 f3): pass environment=')
+            saved_env = meta.get('environment_saved_at')
+            local = [d for d in os.listdir(folder) if d.startswith('Env-')]
+            if local:
+                saved_env = folder + '/' + local[0]
+            assert saved_env is not None, 'The environment was not saved with the agent: pass environment='
+            environment = Environment.load(saved_env)
         if meta['class'] != cls.__name__:
             from .. import agents
             cls = getattr(agents, meta['class'])
@@ -266,4 +271,40 @@ class PBVI_Agent(BeliefSimulationMixin, Agent):
         return inst
 
     def modify_environment(self, new_environment: Environment):
-        raise NotImplementedError('modify_environment (cv2 alpha resampling) is SURVEY §8 f3 ("next")')
+        '''
+        A new agent on a modified environment; the alpha vectors are resampled to the new grid like the reference does
+        (agents/pbvi_agent.py:661-695: cv2.resize of every alpha vector, bilinear with pixel-centre alignment).
+        '''
+        modified = self.__class__(environment=new_environment, thresholds=self.thresholds, name=self.name)
+        if self.value_function is not None:
+            H, W = self.model.grid_shape
+            H2, W2 = modified.model.grid_shape
+            av = self.value_function.alpha_vector_array.reshape(len(self.value_function), H, W)
+            resized = np.array([_resize_bilinear(a, (H2, W2)).ravel() for a in av])
+            modified.value_function = ValueFunction(modified.model, alpha_vectors=resized, action_list=self.value_function.actions)
+            modified.trained, modified.trained_at = self.trained, self.trained_at
+        return modified
+
+
+def _resize_bilinear(a: np.ndarray, new_shape: tuple) -> np.ndarray:
+    'cv2.resize(a, (W2, H2)) (INTER_LINEAR, pixel centres aligned); NumPy fallback with the same convention when cv2 is absent.'
+    try:
+        import cv2
+        return cv2.resize(np.ascontiguousarray(a, dtype=np.float64), (int(new_shape[1]), int(new_shape[0])))
+    except ImportError:
+        pass
+    H, W = a.shape
+    H2, W2 = new_shape
+
+    def axis(n, m):
+        x = (np.arange(m) + 0.5) * (n / m) - 0.5
+        x0 = np.floor(x).astype(int)
+        f = x - x0
+        lo, hi = np.clip(x0, 0, n - 1), np.clip(x0 + 1, 0, n - 1)
+        f = np.where(x0 < 0, 0.0, f)
+        return lo, hi, f
+    ylo, yhi, fy = axis(H, H2)
+    xlo, xhi, fx = axis(W, W2)
+    top = a[ylo][:, xlo] * (1 - fx)[None, :] + a[ylo][:, xhi] * fx[None, :]
+    bot = a[yhi][:, xlo] * (1 - fx)[None, :] + a[yhi][:, xhi] * fx[None, :]
+    return top * (1 - fy)[:, None] + bot * fy[:, None]

@@ -7,7 +7,8 @@ geometry (margins / shape / data bounds / source, :277-377), start probabilities
 (`olfnav_env_step`, include/olfnav_b200.h); the NumPy versions here are the host API the
 reference exposes and are what `exact_converter` uses to build the move table.
 
-Out of scope (raise NotImplementedError): h5 files, layers, `shape=` /
+shape= / multiplier= resampling, save / load and modify / modify_scale are host-side one-offs kept in
+NumPy / SciPy.  Out of scope (raise NotImplementedError): h5 files, layers, `shape=` /
 `multiplier=` resampling, save/load, plotting, modify()/modify_scale().
 '''
 from __future__ import annotations
@@ -19,6 +20,18 @@ import numpy as np
 from .util import get_rng
 
 _BOUNDARIES = ('stop', 'clip', 'wrap', 'wrap_vertical', 'wrap_horizontal')
+
+
+def _resize_array(array: np.ndarray, new_shape: tuple, interpolation: str) -> np.ndarray:
+    '''
+    Resample a 2-D frame onto new_shape with endpoints aligned (index 0 -> 0, last -> last), the convention of the
+    reference's _resize_array (environment.py:25-55, scipy RegularGridInterpolator over linspace indices).
+    '''
+    from scipy.interpolate import RegularGridInterpolator
+    axes = [np.linspace(0, n - 1, n) for n in array.shape]
+    new_axes = [np.linspace(0, n - 1, m) for n, m in zip(array.shape, new_shape)]
+    grid = np.meshgrid(*new_axes, indexing='ij')
+    return RegularGridInterpolator(tuple(axes), array, method=interpolation)(tuple(grid))
 
 
 class Environment:
@@ -38,8 +51,6 @@ class Environment:
                  name: str = None) -> None:
         if layers not in (False, None):
             raise NotImplementedError('layered environments are out of scope of the B200 hot path (SURVEY §8 f4)')
-        if shape is not None or not np.allclose(np.asarray(multiplier, dtype=float), 1.0):
-            raise NotImplementedError('shape= / multiplier= resampling is out of scope of the B200 hot path (SURVEY §8 f3)')
 
         if isinstance(data_file, str):
             if not data_file.endswith('.npy'):
@@ -54,6 +65,8 @@ class Environment:
         assert data.ndim == 3, 'data must have shape (time, y, x)'
 
         self._data = np.ascontiguousarray(data, dtype=np.float64)
+        self._original_data = self._data
+        self._preprocess_data = preprocess_data
         self.saved_at = None
         self.layers, self.layer_labels, self.has_layers = None, None, False
         self.timesteps = int(self._data.shape[0])
@@ -77,6 +90,36 @@ class Environment:
                 raise ValueError('The array or lists of Margins provided have a shape not supported. (Supported formats (2,) or (2,2))')
         assert self.margins.dtype.kind == 'i', 'margins should be integers'
 
+        # shape= / multiplier= (environment.py:293-337): the data zone is resampled to shape - margins, then scaled around the
+        # source by `multiplier` (the margins absorb the difference), every frame by the same separable interpolation as the
+        # reference's _resize_array (environment.py:25-55).  Done once here: the device path needs dense frames in HBM.
+        original_data_shape = self.data_shape
+        new_data_shape = None
+        if shape is not None:
+            shape = np.array(shape)
+            assert np.all(shape > np.sum(self.margins, axis=1)), 'The shape of the environment must be strictly larger than the sum of margins.'
+            new_data_shape = (shape - np.sum(self.margins, axis=1)).astype(int)
+            self.data_source_position = (self.data_source_position * (new_data_shape / np.array(self.data_shape))).astype(int)
+            self.data_shape = tuple(int(v) for v in new_data_shape)
+        else:
+            shape = np.array(self.data_shape) + np.sum(self.margins, axis=1)
+        multiplier = np.array(multiplier, dtype=float)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            low_max = (self.margins[:, 0] / self.data_source_position) + 1
+            high_max = 1 + (self.margins[:, 1] / (np.array(self.data_shape) - self.data_source_position))
+            max_mult = np.min(np.vstack([low_max, high_max]), axis=0)
+        assert np.all(multiplier <= max_mult), f'The multiplier given is larger than allowed (the values should be lower than {max_mult})'
+        scaled_shape = (np.array(self.data_shape) * multiplier).astype(int)
+        new_source = (self.data_source_position * multiplier).astype(int)
+        self.margins = self.margins.copy()
+        self.margins[:, 0] -= (new_source - self.data_source_position)
+        self.margins[:, 1] = shape - (self.margins[:, 0] + scaled_shape)
+        self.data_source_position = new_source
+        self.data_shape = tuple(int(v) for v in scaled_shape)
+        if self.data_shape != original_data_shape:
+            self._data = np.stack([_resize_array(frame, self.data_shape, interpolation_method.lower()) for frame in self._data])
+        self.data_processed = True
+
         self.shape = tuple(int(d + lo + hi) for d, (lo, hi) in zip(self.data_shape, self.margins))
         self.data_bounds = np.stack([self.margins[:, 0], self.margins[:, 0] + np.array(self.data_shape)], axis=1)
         self.source_position = self.data_source_position + self.margins[:, 0]
@@ -88,6 +131,8 @@ class Environment:
         # start probabilities (environment.py:383-423)
         inner = tuple(slice(int(lo), int(hi)) for lo, hi in self.data_bounds)
         probs = np.zeros(self.shape)
+        if isinstance(start_zone, str) and start_zone.startswith('custom_'):       # a start_type string handed back by modify()
+            start_zone = np.array(start_zone.split('_')[1:]).reshape((2, 2)).astype(int)
         self.start_type = start_zone if isinstance(start_zone, str) else 'custom'
         if isinstance(start_zone, np.ndarray):
             if start_zone.shape == (2, 2):
@@ -101,7 +146,12 @@ class Environment:
             probs[inner] = 1.0
         elif start_zone == 'odor_present':
             thr = 0 if odor_present_threshold is None else odor_present_threshold
-            probs[inner] = (np.mean((self._data > thr).astype(int), axis=0) > 0).astype(float)
+            if self.data_shape != original_data_shape and not preprocess_data:
+                # reference quirk (environment.py:402-413): on lazily resampled data the map is the FRACTION of frames with odor,
+                # not the 0/1 indicator used for data that is already at its final shape
+                probs[inner] = np.mean((self._data > thr).astype(float), axis=0)
+            else:
+                probs[inner] = (np.mean((self._data > thr).astype(int), axis=0) > 0).astype(float)
         else:
             raise ValueError('start_zone value is wrong')
         self.odor_present_threshold = odor_present_threshold
@@ -199,6 +249,106 @@ class Environment:
             raise NotImplementedError('This distance metric has not yet been implemented')
         d = np.sum(np.abs(self.source_position[None, :] - p), axis=-1) - self.source_radius
         return float(d[0]) if single else d
+
+    # -- persistence and variants (environment.py:809-996, :1061-1161) ---------------------------------
+    def save(self, folder: str = None, save_arrays: bool = False, force: bool = False) -> None:
+        'METADATA.json (+ data.npy, start_probabilities.npy with save_arrays) in <folder>/Env-<name>; same keys as the reference.'
+        import json, os, shutil
+        assert save_arrays or ((self.data_file_path is not None) and (self.start_type is not None)), \
+            "The environment was not created from a data file so 'save_arrays' has to be set to True."
+        folder = f'./Env-{self.name}' if folder is None else folder + '/Env-' + self.name
+        if not os.path.exists(folder):
+            os.mkdir(folder)
+        elif len(os.listdir(folder)) > 0:
+            if not force:
+                raise Exception(f'{folder} is not empty. If you want to overwrite the saved environment, enable "force".')
+            shutil.rmtree(folder)
+            os.mkdir(folder)
+        if self.start_type.startswith('custom') and len(self.start_type.split('_')) == 1 and not save_arrays:
+            raise Exception('Start probabilities have been set from a custom array, please enable save_arrays to be able to reconstruct the environment later.')
+        arguments = {'name': self.name}
+        if self.data_file_path is not None:
+            arguments['data_file_path'] = self.data_file_path
+        arguments.update(timesteps=int(self.timesteps), data_shape=list(self.data_shape), dimensions=self.dimensions,
+                         margins=self.margins.tolist(), shape=list(self.shape), data_bounds=self.data_bounds.tolist(),
+                         original_data_source_position=np.asarray(self.original_data_source_position).tolist(),
+                         data_source_position=self.data_source_position.tolist(), layers=False,
+                         source_position=self.source_position.tolist(), source_radius=self.source_radius,
+                         interpolation_method=self.interpolation_method, preprocess_data=self._preprocess_data,
+                         data_processed=self.data_processed, boundary_condition=self.boundary_condition, start_type=self.start_type)
+        if self.odor_present_threshold is not None:
+            arguments['odor_present_threshold'] = self.odor_present_threshold
+        with open(folder + '/METADATA.json', 'w') as f:
+            json.dump(arguments, f, indent=4)
+        if save_arrays:
+            np.save(folder + '/data.npy', self._data)
+            np.save(folder + '/start_probabilities.npy', self.start_probabilities)
+        self.saved_at = os.path.abspath(folder).replace('\\', '/')
+        print(f'Environment saved to: {folder}')
+
+    @classmethod
+    def load(cls, folder: str) -> 'Environment':
+        import json, os
+        assert os.path.exists(folder), "Folder doesn't exist..."
+        assert folder.rstrip('/').split('/')[-1].startswith('Env-'), 'The folder provided is not the data of en Environment object.'
+        with open(folder + '/METADATA.json', 'r') as f:
+            a = json.load(f)
+        if os.path.exists(folder + '/data.npy') and os.path.exists(folder + '/start_probabilities.npy'):
+            env = cls.__new__(cls)
+            env._data = np.ascontiguousarray(np.load(folder + '/data.npy'), dtype=np.float64)
+            env.start_probabilities = np.load(folder + '/start_probabilities.npy')
+            env.name, env.timesteps, env.dimensions = a['name'], a['timesteps'], a['dimensions']
+            env.data_shape, env.shape = tuple(a['data_shape']), tuple(a['shape'])
+            env.margins, env.data_bounds = np.array(a['margins']), np.array(a['data_bounds'])
+            env.original_data_source_position = np.array(a['original_data_source_position'])
+            env.data_source_position, env.source_position = np.array(a['data_source_position']), np.array(a['source_position'])
+            env.source_radius = a['source_radius']
+            env.has_layers, env.layers, env.layer_labels = False, None, None
+            env.interpolation_method, env._preprocess_data, env.data_processed = a['interpolation_method'], a['preprocess_data'], True
+            env.boundary_condition = a['boundary_condition']
+            env.data_file_path, env.odor_present_threshold, env.start_type = a.get('data_file_path'), a.get('odor_present_threshold'), a.get('start_type')
+            env.is_on_gpu, env._device_handles, env.reference_time_quirk = False, {}, True
+        else:
+            start_zone = a['start_type']
+            bounds = None
+            if start_zone.startswith('custom'):
+                bounds = np.array(start_zone.split('_')[1:]).reshape((a['dimensions'], 2)).astype(int)
+            env = cls(data_file=a['data_file_path'], data_source_position=a['original_data_source_position'], source_radius=a['source_radius'],
+                      layers=a['layers'], shape=a['shape'], margins=a['margins'], interpolation_method=a['interpolation_method'],
+                      preprocess_data=a['preprocess_data'], boundary_condition=a['boundary_condition'],
+                      start_zone=(bounds if bounds is not None else start_zone), odor_present_threshold=a.get('odor_present_threshold'),
+                      name=a['name'])
+        env.saved_at = os.path.abspath(folder)
+        return env
+
+    def _source_data(self):
+        'What a modified copy is rebuilt from: the data file, else the ORIGINAL (unresampled) frames.'
+        return self.data_file_path if self.data_file_path is not None else self._original_data
+
+    def modify(self, data_source_position=None, source_radius: float = None, shape=None, margins=None, multiplier=None,
+               interpolation_method: str = None, boundary_condition: str = None) -> 'Environment':
+        'A copy with one or more parameters changed (environment.py:1061-1123).'
+        return Environment(data_file=self._source_data(),
+                           data_source_position=(data_source_position if data_source_position is not None else self.original_data_source_position),
+                           source_radius=(source_radius if source_radius is not None else self.source_radius),
+                           layers=False,
+                           shape=(shape if shape is not None else self.shape),
+                           margins=(margins if margins is not None else self.margins),
+                           multiplier=(multiplier if multiplier is not None else [1.0, 1.0]),
+                           interpolation_method=(interpolation_method if interpolation_method is not None else self.interpolation_method),
+                           preprocess_data=self._preprocess_data,
+                           boundary_condition=(boundary_condition if boundary_condition is not None else self.boundary_condition),
+                           start_zone=self.start_type, odor_present_threshold=self.odor_present_threshold, name=self.name)
+
+    def modify_scale(self, scale_factor: float) -> 'Environment':
+        'Everything scaled by one factor: shape, margins, source radius and data shape (environment.py:1126-1161).'
+        return Environment(data_file=self._source_data(), data_source_position=self.original_data_source_position,
+                           source_radius=self.source_radius * scale_factor, layers=False,
+                           shape=(np.array(self.shape) * scale_factor).astype(int),
+                           margins=(self.margins * scale_factor).astype(int), multiplier=[1.0, 1.0],
+                           interpolation_method=self.interpolation_method, preprocess_data=self._preprocess_data,
+                           boundary_condition=self.boundary_condition, start_zone=self.start_type,
+                           odor_present_threshold=self.odor_present_threshold, name=self.name)
 
     # -- device side -----------------------------------------------------------------------------
     def device_handle(self, device: int):

@@ -209,3 +209,34 @@ def test_fsvi_matches_oracle_solver_alpha_count():
     A_d, A_o = vf_d.alpha_vector_array, vf_o.alpha_vector_array
     matched = sum(np.any(np.all(np.isclose(A_d, a[None, :], rtol=1e-4, atol=1e-6), axis=1)) for a in A_o)
     assert matched >= 0.8 * len(A_o)
+
+
+def test_robustness_flow_modified_environment():
+    '''
+    SURVEY §8 f3 / test_setups.py:421-429,646-654: an agent trained on one environment is run in a rescaled one (the device
+    env step takes the TEST environment, the belief kernels the agent's model), and an agent moved to the new environment with
+    modify_environment runs on its own grid.  The fused device loop must reproduce the host-driven protocol loop exactly.
+    '''
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200 import simulation
+    c = onb.synthetic.config('T1')
+    env = onb.Environment(**c['env_kwargs'])
+    agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=3)
+    agent.train(expansions=5, print_progress=False, print_stats=False)
+    n, horizon = 40, 50
+    for big, ag in ((env.modify_scale(1.5), agent), (env.modify_scale(1.5), None)):
+        if ag is None:
+            ag = agent.modify_environment(big)
+            assert ag.model.grid_shape == big.shape and len(ag.value_function) == len(agent.value_function)
+        starts = big.random_start_points(n, np.random.default_rng(4))
+        tshift = np.random.default_rng(5).integers(0, big.timesteps, n)
+        if ag is agent:
+            # the agent's grid is smaller than the test environment: keep the start points inside the agent's grid
+            starts = np.minimum(starts, np.array(env.shape)[None, :] - 1)
+        dev = onb.run_test(ag, n=n, start_points=starts, time_shift=tshift, environment=big, horizon=horizon, print_progress=False,
+                           print_stats=False, print_warning=False, batches=1)
+        host = simulation._run_generic(ag, n, starts, tshift.astype(int), environment=big, time_loop=True, horizon=horizon,
+                                       initialization_values={}, reward_discount=0.99, distance_metric='l1', print_progress=False)
+        assert np.array_equal(dev.done_at_step, host.done_at_step) and np.array_equal(dev.reached_source, host.reached_source)
+        assert np.array_equal(np.array(dev.positions), np.array(host.positions))
+        assert np.array_equal(np.array(dev.actions), np.array(host.actions))
