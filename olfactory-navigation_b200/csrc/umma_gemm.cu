@@ -2,7 +2,8 @@
 // max/argmax epilogue.  Serves
 //   * ValueFunction.evaluate_at   (reference agents/pbvi_agent.py:741):  beliefs (N x S) x alphas (S x G)
 //   * the PBVI backup contraction (inside solvers.*.solve, reference agents/fsvi_agent.py:201-224):
-//     beliefs (B x S) x Gamma_{a,o} (S x G*A*O), argmax over g inside every (a,o) segment.
+//     beliefs (B x S) x Gamma_{a,o} (S x G*A*O), argmax over g inside every (a,o) segment
+//   * the infotaxis sums (reference agents/infotaxis_agent.py:271-274): beliefs x pull tables, plain store epilogue.
 //
 // D (128 x BN, FP32, in TMEM) += A_hi·B_hi + A_lo·B_hi + A_hi·B_lo per K block of 32, where x_hi is x with the
 // low 13 mantissa bits cleared (exactly TF32) and x_lo = trunc_tf32(x - x_hi).  The dropped terms are
@@ -13,11 +14,11 @@
 // accumulator therefore only lives for KCHUNK k-blocks (48 MMAs); the epilogue warps then add the partial
 // sums into FP32 registers (round to nearest) while the MMA warp fills the other TMEM buffer.
 //
-// Warp roles (384 threads, one CTA per SM, persistent over 128-row tiles of A):
+// Warp roles (384 threads, one CTA per SM, persistent over (m tile, n tile) work units):
 //   warp 0      TMA producer: A tile (raw FP32) + B_hi + B_lo tiles, 128B swizzle, mbarrier complete_tx
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32, tcgen05.commit frees stages
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory)
 //   warp 2      TMEM allocator
-//   warps 4-7   A transform: split the raw tile in place into hi (same buffer) and lo (second buffer)
+//   warps 4-7   A transform: raw FP32 row (shared memory) -> hi / lo in tensor memory (tcgen05.st)
 //   warps 8-11  epilogue: tcgen05.ld each K-chunk's partial accumulator, FP32 register sums, segmented max/argmax
 // Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
 #include "common.cuh"
@@ -47,9 +48,6 @@ struct GemmParams {
                                  // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
     float* out_store;            // != NULL: store mode, out_store[row * out_ld + col] = product (col < rows_b); no max / argmax
     long long out_ld;
-    int pair;                    // the producer issues the A loads of `pair` consecutive k-blocks together (same DRAM pages)
-    int dbg;                     // timing experiments only (OLFNAV_GEMM_DBG bitmask): 1 no B loads, 2 no MMA issue, 8 no TMEM loads
-    int raw_hi;                  // 1: leave the raw FP32 A tile as the "hi" operand (the tensor core ignores the low 13 mantissa bits)
 };
 
 // unit id -> (m tile, n tile)
@@ -119,11 +117,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // A operand in tensor memory (TS form): lane = row of A, 8 consecutive 32-bit columns = the K = 8 slice
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -170,248 +163,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN, int STAGES>
-struct SmemLayout {
-    static constexpr int B_TILE_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for 1024-byte alignment
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1)
-umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                   const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
-    using L = SmemLayout<BN, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-
-    auto a_hi = [&](int s) { return base + s * L::STAGE_BYTES; };
-    auto a_lo = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES; };
-    auto b_hi = [&](int s) { return base + s * L::STAGE_BYTES + 2 * A_TILE_BYTES; };
-    auto b_lo = [&](int s) { return base + s * L::STAGE_BYTES + 2 * A_TILE_BYTES + L::B_TILE_BYTES; };
-    const uint32_t bars = base + L::BAR_OFFSET;
-    auto bar_full = [&](int s) { return bars + 8 * s; };
-    auto bar_ready = [&](int s) { return bars + 8 * (STAGES + s); };
-    auto bar_empty = [&](int s) { return bars + 8 * (2 * STAGES + s); };
-    auto bar_tfull = [&](int a) { return bars + 8 * (3 * STAGES + a); };
-    auto bar_tempty = [&](int a) { return bars + 8 * (3 * STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * (3 * STAGES + 4));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));   // power of two >= 32
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBhi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmBlo) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 128); mbar_init(bar_empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int KB = p.num_k_blocks;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one_sync()) {
-            uint32_t it = 0;
-            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-                int mt, nt;
-                unit_to_tile(p, u, mt, nt);
-                const int pair = (p.pair > 1 && p.pair <= STAGES / 2) ? p.pair : 1;
-                for (int kb0 = 0; kb0 < KB; kb0 += pair) {
-                    const int np = min(pair, KB - kb0);
-                    // A first, for all k-blocks of the group: their 128-byte pieces are adjacent in every belief row
-                    for (int j = 0; j < np; ++j) {
-                        const int s = (it + j) % STAGES;
-                        const uint32_t ph = ((it + j) / STAGES) & 1;
-                        mbar_wait(bar_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_full(s), A_TILE_BYTES + ((p.dbg & 1) ? 0 : 2 * L::B_TILE_BYTES));
-                        tma_load_2d(a_hi(s), &tmA, (kb0 + j) * BK, mt * BM, bar_full(s));
-                    }
-                    for (int j = 0; j < np && !(p.dbg & 1); ++j) {
-                        const int s = (it + j) % STAGES;
-                        tma_load_2d(b_hi(s), &tmBhi, (kb0 + j) * BK, nt * BN, bar_full(s));
-                        tma_load_2d(b_lo(s), &tmBlo, (kb0 + j) * BK, nt * BN, bar_full(s));
-                    }
-                    it += np;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_tf32<BN>();
-        uint32_t it = 0, ccount = 0;
-        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
-                const int acc = ccount & 1;
-                const uint32_t aph = (ccount >> 1) & 1;
-                mbar_wait(bar_tempty(acc), aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                const int kb1 = min(KB, kb0 + KCHUNK);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(bar_ready(s), ph);
-                    tc_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t dah = make_sw128_desc(a_hi(s)), dal = make_sw128_desc(a_lo(s));
-                        const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
-#pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K && !(p.dbg & 2) && !((p.dbg & 4) && (kb & 1)); ++kk) {
-                            const uint64_t adv = (uint64_t)(kk * UMMA_K * 4 / 16);   // +32 B per K step inside the swizzle row
-                            tc_mma_tf32(d_tmem, dah + adv, dbh + adv, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-                            if (p.raw_hi == 3) continue;             // timing experiment only: 1xTF32
-                            tc_mma_tf32(d_tmem, dal + adv, dbh + adv, idesc, 1u);
-                            tc_mma_tf32(d_tmem, dah + adv, dbl + adv, idesc, 1u);
-                        }
-                        if (p.dbg & 16) mbar_arrive(bar_empty(s));   // timing experiment only: frees the stage without waiting for the MMAs
-                        else tc_commit(bar_empty(s));                 // frees the stage once these MMAs retire
-                        if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== A transform: raw FP32 -> (hi in place, lo) =====================
-        // All eight 16-byte pieces of a thread are loaded before the first one is split, so the shared-memory latency is paid once
-        // per stage.  The split is elementwise, so the 128B swizzle of the tile is irrelevant here.
-        const int t = threadIdx.x - 128;
-        constexpr int PIECES = A_TILE_BYTES / 16 / 128;
-        uint32_t it = 0;
-        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_full(s), ph);
-                float4* ah = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES) + t;
-                float4* al = reinterpret_cast<float4*>(gbase + s * L::STAGE_BYTES + A_TILE_BYTES) + t;
-                float4 v[PIECES];
-                if (p.raw_hi == 2) {      // timing experiment only: no split at all (results are 1xTF32)
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(bar_ready(s));
-                    continue;
-                }
-#pragma unroll
-                for (int i = 0; i < PIECES; ++i) v[i] = ah[128 * i];
-#pragma unroll
-                for (int i = 0; i < PIECES; ++i) {
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
-                    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
-                    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
-                    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
-                    l.x = __uint_as_float(__float_as_uint(v[i].x - h.x) & 0xffffe000u);
-                    l.y = __uint_as_float(__float_as_uint(v[i].y - h.y) & 0xffffe000u);
-                    l.z = __uint_as_float(__float_as_uint(v[i].z - h.z) & 0xffffe000u);
-                    l.w = __uint_as_float(__float_as_uint(v[i].w - h.w) & 0xffffe000u);
-                    if (!p.raw_hi) ah[128 * i] = h;
-                    al[128 * i] = l;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
-                mbar_arrive(bar_ready(s));
-            }
-        }
-    } else if (warp >= 8) {
-        // ===================== epilogue: FP32 register accumulation + segmented max / argmax =====================
-        const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const bool direct = p.ws == nullptr;         // one n tile covers all columns: write the results directly
-        uint32_t ccount = 0;
-        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            int mt, nt;
-            unit_to_tile(p, u, mt, nt);
-            const long long row = (long long)mt * BM + q * 32 + lane;
-            const bool row_ok = row < p.n_rows;
-            const int col0 = nt * BN;
-            int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;   // current segment and index inside its stride
-            float best = -INFINITY;
-            int best_idx = 0;
-            bool dirty = false;
-            float sum[BN];
-#pragma unroll
-            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
-                const int acc = ccount & 1;
-                const uint32_t aph = (ccount >> 1) & 1;
-                mbar_wait(bar_tfull(acc), aph);
-                tc_fence_after();
-                if (p.dbg & 8) {
-                } else if constexpr (BN >= 112 || (BN % 32) != 0) {       // 16-column loads: odd multiples of 16, and wide tiles whose running sums fill the register file
-#pragma unroll
-                    for (int c0 = 0; c0 < BN; c0 += 16) {
-                        uint32_t v[16];
-                        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int c0 = 0; c0 < BN; c0 += 32) {
-                        uint32_t v[32];
-                        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(bar_tempty(acc));
-            }
-            if (p.out_store) {
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < BN; ++j)
-                        if (col0 + j < p.rows_b) p.out_store[row * p.out_ld + col0 + j] = sum[j];
-                }
-                continue;
-            }
-            auto flush = [&]() {
-                if (row_ok && cur_seg < p.n_seg) {
-                    if (direct) {
-                        p.out_val[row * p.n_seg + cur_seg] = best;
-                        p.out_arg[row * p.n_seg + cur_seg] = best_idx;
-                    } else if (dirty) {
-                        atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
-                    }
-                }
-            };
-#pragma unroll
-            for (int j = 0; j < BN; ++j) {
-                const float x = sum[j];
-                if (r < p.seg_len && cur_seg < p.n_seg) {
-                    dirty = true;
-                    if (x > best) { best = x; best_idx = r; }
-                }
-                if (++r == p.seg_stride) {
-                    flush();
-                    r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
-                }
-            }
-            if (r != 0 && !direct) flush();          // the segment continues in another unit
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // ============================================================================================================
 // v3: A operand in TENSOR MEMORY.  Measured on B200 (scripts/umma_rate_bench.cu, OLFNAV_GEMM_DBG experiments): with both
 // operands in shared memory the kernel is bound by the 128 B/clk shared-memory port — TMA writes, the hi/lo transform's
@@ -420,21 +171,23 @@ umma_segmax_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // registers and write hi and lo straight into tensor memory (tcgen05.st); the MMAs take A from TMEM and only B from shared
 // memory.  Shared memory per stage shrinks to the raw A tile + the two B planes, so more stages fit.
 //   TMEM columns: [0, 2*BN) two accumulator buffers, [A_BASE + 64*s, +32) hi and (+32, +64) lo of stage s.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TA>
 struct SmemLayoutTS {
     static constexpr int B_TILE_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
     static constexpr int A_BASE = BN <= 64 ? 128 : 256;
-    static_assert(A_BASE + 64 * STAGES <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
+    static constexpr int NUM_BARS = 3 * STAGES + 4 + TA;
+    static_assert(A_BASE + 64 * TA <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
+    static_assert(TOTAL <= 227 * 1024 && 8 * NUM_BARS + 8 <= 256, "shared memory budget");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
-    using L = SmemLayoutTS<BN, STAGES>;
+    using L = SmemLayoutTS<BN, STAGES, TA>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -448,7 +201,8 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto bar_empty = [&](int s) { return bars + 8 * (2 * STAGES + s); };
     auto bar_tfull = [&](int a) { return bars + 8 * (3 * STAGES + a); };
     auto bar_tempty = [&](int a) { return bars + 8 * (3 * STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * (3 * STAGES + 4));
+    auto bar_aempty = [&](int a) { return bars + 8 * (3 * STAGES + 4 + a); };     // TMEM A slot a has been read by its MMAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * L::NUM_BARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 512;
@@ -461,6 +215,7 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 128); mbar_init(bar_empty(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        for (int a = 0; a < TA; ++a) mbar_init(bar_aempty(a), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -509,7 +264,8 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(bar_ready(s), ph);
                     tc_fence_after();
                     if (elect_one_sync()) {
-                        const uint32_t ah = tmem_base + L::A_BASE + 64 * s, al = ah + 32;
+                        const int ta = it % TA;
+                        const uint32_t ah = tmem_base + L::A_BASE + 64 * ta, al = ah + 32;
                         const uint64_t dbh = make_sw128_desc(b_hi(s)), dbl = make_sw128_desc(b_lo(s));
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
@@ -518,7 +274,8 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tc_mma_tf32_ts(d_tmem, al + kk * UMMA_K, dbh + adv, idesc, 1u);
                             tc_mma_tf32_ts(d_tmem, ah + kk * UMMA_K, dbl + adv, idesc, 1u);
                         }
-                        tc_commit(bar_empty(s));                 // frees the stage (shared memory and its TMEM slot) once these MMAs retire
+                        tc_commit(bar_empty(s));                 // frees the shared-memory stage once these MMAs retire
+                        tc_commit(bar_aempty(ta));               // ... and the TMEM slot of A
                         if (kb == kb1 - 1) tc_commit(bar_tfull(acc));
                     }
                     __syncwarp();
@@ -538,11 +295,12 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
+                const int ta = it % TA;
                 mbar_wait(bar_full(s), ph);
-                // (the stage's TMEM slot is free: bar_empty(s) completed before the producer refilled the stage)
+                mbar_wait(bar_aempty(ta), ((it / TA) & 1) ^ 1);
                 tc_fence_after();
                 const uint8_t* src = rowp + s * L::STAGE_BYTES;
-                const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * s;
+                const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * ta;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float4 v[4];
@@ -696,28 +454,15 @@ int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t out
     return OLFNAV_OK;
 }
 
-template <int BN, int STAGES>
-int launch(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl, const GemmParams& p, int grid, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-        OLF_CUDA(cudaFuncSetAttribute(umma_segmax_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
-    umma_segmax_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
-    OLF_LAUNCH_CHECK();
-    return OLFNAV_OK;
-}
-
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TA>
 int launch_ts(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl, const GemmParams& p, int grid, cudaStream_t st) {
-    using L = SmemLayoutTS<BN, STAGES>;
+    using L = SmemLayoutTS<BN, STAGES, TA>;
     static bool configured = false;
     if (!configured) {
-        OLF_CUDA(cudaFuncSetAttribute(umma_ts_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        OLF_CUDA(cudaFuncSetAttribute(umma_ts_kernel<BN, STAGES, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    umma_ts_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
+    umma_ts_kernel<BN, STAGES, TA><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
 }
@@ -735,10 +480,6 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     p.num_k_blocks = olf_div_up(K, BK);
     p.num_units = p.num_m_tiles * p.num_n_tiles;
     p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
-    static const int raw_hi = [] { const char* e = getenv("OLFNAV_GEMM_RAWHI"); return e ? atoi(e) : 0; }();
-    p.raw_hi = raw_hi;
-    static const int dbg = [] { const char* e = getenv("OLFNAV_GEMM_DBG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
     p.ws = nullptr;
     const size_t n_out = (size_t)n_rows * p.n_seg;
     if (!p.out_store && p.num_n_tiles > 1) {
@@ -747,45 +488,23 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     }
 
     CUtensorMap tA, tBh, tBl;
-    // A streams from HBM in 128-byte pieces per belief row (row stride ~123 KB): let L2 fetch 256 B per miss, so that every second
-    // k-block of a row is an L2 hit and the DRAM row-activate rate halves (OLFNAV_GEMM_APROMO = 64 | 128 | 256, default 256)
-    static const CUtensorMapL2promotion a_promo = [] {
-        const char* e = getenv("OLFNAV_GEMM_APROMO");
-        const int v = e ? atoi(e) : 256;
-        return v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    }();
-    static const int pair_env = [] { const char* e = getenv("OLFNAV_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-    p.pair = pair_env;
-    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM, a_promo);
+    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
 
     const int grid = p.num_units < sm_count ? p.num_units : sm_count;
-    static const bool force_ss = [] { const char* e = getenv("OLFNAV_GEMM_SS"); return e && e[0] == '1'; }();
-    if (!force_ss) {
-        // A in tensor memory: stage = 16 KB raw A + 2 B planes of BN x 128 B; TMEM holds 64 columns of hi / lo per stage
-        switch (BN) {
-            case 16:  rc = launch_ts<16, 6>(tA, tBh, tBl, p, grid, st); break;
-            case 32:  rc = launch_ts<32, 6>(tA, tBh, tBl, p, grid, st); break;
-            case 48:  rc = launch_ts<48, 6>(tA, tBh, tBl, p, grid, st); break;
-            case 64:  rc = launch_ts<64, 6>(tA, tBh, tBl, p, grid, st); break;
-            case 80:  rc = launch_ts<80, 4>(tA, tBh, tBl, p, grid, st); break;
-            case 96:  rc = launch_ts<96, 4>(tA, tBh, tBl, p, grid, st); break;
-            case 112: rc = launch_ts<112, 4>(tA, tBh, tBl, p, grid, st); break;
-            default:  rc = launch_ts<128, 4>(tA, tBh, tBl, p, grid, st); break;
-        }
-    } else
-    // stages: as many as fit ~220 KB of shared memory (stage = 32 KB of A planes + 2 B planes of BN x 128 B)
+    // A in tensor memory: shared-memory stage = 16 KB raw A + 2 B planes of BN x 128 B (as many as fit ~216 KB);
+    // TMEM holds 64 columns (hi, lo) per A slot next to the two accumulator buffers (512 columns in all)
     switch (BN) {
-        case 16:  rc = launch<16, 6>(tA, tBh, tBl, p, grid, st); break;
-        case 32:  rc = launch<32, 5>(tA, tBh, tBl, p, grid, st); break;
-        case 48:  rc = launch<48, 4>(tA, tBh, tBl, p, grid, st); break;
-        case 64:  rc = launch<64, 4>(tA, tBh, tBl, p, grid, st); break;
-        case 80:  rc = launch<80, 4>(tA, tBh, tBl, p, grid, st); break;
-        case 96:  rc = launch<96, 3>(tA, tBh, tBl, p, grid, st); break;
-        case 112: rc = launch<112, 3>(tA, tBh, tBl, p, grid, st); break;
-        default:  rc = launch<128, 3>(tA, tBh, tBl, p, grid, st); break;
+        case 16:  rc = launch_ts<16, 6, 6>(tA, tBh, tBl, p, grid, st); break;
+        case 32:  rc = launch_ts<32, 6, 6>(tA, tBh, tBl, p, grid, st); break;
+        case 48:  rc = launch_ts<48, 6, 6>(tA, tBh, tBl, p, grid, st); break;
+        case 64:  rc = launch_ts<64, 6, 6>(tA, tBh, tBl, p, grid, st); break;
+        case 80:  rc = launch_ts<80, 6, 4>(tA, tBh, tBl, p, grid, st); break;
+        case 96:  rc = launch_ts<96, 5, 4>(tA, tBh, tBl, p, grid, st); break;
+        case 112: rc = launch_ts<112, 4, 4>(tA, tBh, tBl, p, grid, st); break;
+        default:  rc = launch_ts<128, 4, 4>(tA, tBh, tBl, p, grid, st); break;
     }
     if (p.ws) {
         if (rc == OLFNAV_OK) {

@@ -107,8 +107,8 @@ class Environment:
         with np.errstate(divide='ignore', invalid='ignore'):
             low_max = (self.margins[:, 0] / self.data_source_position) + 1
             high_max = 1 + (self.margins[:, 1] / (np.array(self.data_shape) - self.data_source_position))
-            max_mult = np.min(np.vstack([low_max, high_max]), axis=0)
-        assert np.all(multiplier <= max_mult), f'The multiplier given is larger than allowed (the values should be lower than {max_mult})'
+            max_mult = np.nan_to_num(np.min(np.vstack([low_max, high_max]), axis=0), nan=np.inf)   # 0 / 0: no margin AND source on the edge
+        assert np.all(multiplier == 1.0) or np.all(multiplier <= max_mult), f'The multiplier given is larger than allowed (the values should be lower than {max_mult})'
         scaled_shape = (np.array(self.data_shape) * multiplier).astype(int)
         new_source = (self.data_source_position * multiplier).astype(int)
         self.margins = self.margins.copy()
