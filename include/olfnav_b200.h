@@ -223,6 +223,9 @@ typedef struct olfnav_sim_step_args {
     int32_t time_mode;                                /* 0: each agent its own time; 1: the reference's sorted-time indexing */
     int32_t time_loop;                                /* 1: recordings loop for ever (run_test default) */
     int32_t eval_path;                                /* see olfnav_evaluate */
+    int32_t have_act;                                 /* 1: `act` already holds this step's action ids (the caller ran the policy
+                                                         on b_in ahead of time, overlapping it with its read-back of the previous
+                                                         step's counts): the policy kernels are skipped */
     int32_t* act; int32_t* obs_id; int32_t* src_rows; int32_t* act_c; int32_t* obs_c;
     uint8_t* ok; uint8_t* at_end; uint8_t* term_c;
     int32_t* hist;                                    /* T + 1 ints, time_mode 1 only */

@@ -67,7 +67,7 @@ class SimStepArgs(ctypes.Structure):
         ('n', _i64), ('step', _i64),
         ('moves', _p),
         ('thresholds', _p), ('n_thr', ctypes.c_int32),
-        ('time_mode', ctypes.c_int32), ('time_loop', ctypes.c_int32), ('eval_path', ctypes.c_int32),
+        ('time_mode', ctypes.c_int32), ('time_loop', ctypes.c_int32), ('eval_path', ctypes.c_int32), ('have_act', ctypes.c_int32),
         ('act', _p), ('obs_id', _p), ('src_rows', _p), ('act_c', _p), ('obs_c', _p),
         ('ok', _p), ('at_end', _p), ('term_c', _p),
         ('hist', _p),

@@ -180,8 +180,9 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
     const int grid = olf_div_up(n, 256);
     int rc;
 
-    // 1. policy
-    if (alphas) rc = olf_evaluate_into(m, alphas, a->b_in, a->ld, n, a->scale_in, a->eval_val, a->eval_idx, nullptr, nullptr, a->act, a->eval_path, st);
+    // 1. policy (skipped when the caller already ran it on b_in)
+    if (a->have_act) rc = OLFNAV_OK;
+    else if (alphas) rc = olf_evaluate_into(m, alphas, a->b_in, a->ld, n, a->scale_in, a->eval_val, a->eval_idx, nullptr, nullptr, a->act, a->eval_path, st);
     else        rc = olfnav_infotaxis_choose(m, a->b_in, a->ld, n, a->scale_in, a->act, nullptr, stream);
     if (rc != OLFNAV_OK) return rc;
     if (a->ev_policy_end) OLF_CUDA(cudaEventRecord((cudaEvent_t)a->ev_policy_end, st));

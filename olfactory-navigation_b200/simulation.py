@@ -285,9 +285,10 @@ def _run_batches(agent, n, start_points, time_shift, batches, **kw) -> Simulatio
 def _run_single(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
                 reward_discount, distance_metric, print_progress, record: bool = True, timing: list = None) -> SimulationHistory:
     '''
-    One batch, device resident.  Per step: ONE C-ABI call (olfnav_sim_step: policy -> environment step -> compaction
-    plan -> fused belief update) and one 16-byte read-back of the survivor counts; the O(N) history record of the
-    step is copied to pinned host memory on a side stream while the next step runs.
+    One batch, device resident.  Per step: ONE C-ABI call (olfnav_sim_step: environment step -> compaction plan -> fused
+    belief update), the policy of the next step (value-function evaluation / infotaxis choice) enqueued right behind it, and
+    one 16-byte read-back of the survivor counts that the host waits for while that policy runs; the O(N) history record of
+    the step is copied to pinned host memory on a side stream while the next step runs.
     '''
     from ._lib import SimStepArgs
     from .agents.pbvi_agent import BeliefSimulationMixin
@@ -346,8 +347,18 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                           observations=h_odor.numpy()[:m_rec], reached_source=h_reached.numpy()[:m_rec].astype(bool),
                           interupt=h_term.numpy()[:m_rec].astype(bool), action_is_id=True)
 
+    def run_policy(b, scale, rows: int, act_out) -> None:
+        'argmax_g b.alpha_g -> action id (agents/pbvi_agent.py:741) or the infotaxis choice (agents/infotaxis_agent.py:244-301).'
+        with torch.cuda.device(device):
+            if is_infotaxis:
+                check(lib.olfnav_infotaxis_choose(model_h, b.data_ptr(), b.stride(0), rows, scale.data_ptr(), act_out.data_ptr(), None, stream()))
+            else:
+                check(lib.olfnav_evaluate(model_h, alphas_h, b.data_ptr(), b.stride(0), rows, scale.data_ptr(), None, None, act_out.data_ptr(),
+                                          int(getattr(agent, 'gemm_path', 0)), stream()))
+
     args = SimStepArgs()
     n_live, cur = n, 0
+    have_act = False                   # the next step's actions were computed ahead of time (see the end of the loop body)
     iterator = range(horizon)
     if print_progress:
         try:
@@ -372,6 +383,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.time_mode = 1 if environment.reference_time_quirk else 0
         args.time_loop = 1 if time_loop else 0
         args.eval_path = int(getattr(agent, 'gemm_path', 0))
+        args.have_act = 1 if have_act else 0
         args.act, args.obs_id, args.src_rows, args.act_c, args.obs_c = r['act'].data_ptr(), obs_id.data_ptr(), src_rows.data_ptr(), act_c.data_ptr(), obs_c.data_ptr()
         args.ok, args.at_end, args.term_c = ok.data_ptr(), at_end.data_ptr(), term_c.data_ptr()
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
@@ -390,6 +402,22 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         step_done.record(main)
         if timing is not None:
             evs[4].record(main)
+
+        # Policy of the NEXT step, enqueued before the host waits for this step's survivor count: it runs over the n_live rows of
+        # the updated buffer (an upper bound of the survivors; rows are independent, the surplus results are never read) and keeps
+        # the GPU busy while the host reads the counts and prepares the next call.
+        have_act = i + 1 < horizon
+        if have_act:
+            nxt = recs[(i + 1) & 1]
+            if rec_free[(i + 1) & 1] is not None:
+                main.wait_event(rec_free[(i + 1) & 1])
+            if timing is not None:
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record(main)
+            run_policy(b_nxt, s_nxt, n_live, nxt['act'])
+            if timing is not None:
+                p1.record(main)
+                evs += [p0, p1]
 
         # record of this step -> pinned host memory on the side stream
         bufs = None if not record else (torch.empty(n_live, dtype=torch.int32, pin_memory=True), torch.empty((n_live, 2), dtype=torch.int32, pin_memory=True),
@@ -423,6 +451,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             if k:
                 pos[1 - cur][:k] = pos[cur][:m][rows]
                 ts[1 - cur][:k] = ts[cur][:m][rows]
+                if have_act:
+                    nxt['act'][:k] = nxt['act'][:m][rows]
             cur = 1 - cur
             agent.kill_device(~keep)
             m = k
