@@ -36,6 +36,9 @@ class BeliefSimulationMixin:
         model: POMDP = self.model
         Sp = model.padded_states
         self._device = device
+        # release the buffers of a previous run BEFORE allocating the new ones: two belief buffers of a C5 shard are 2 x 61.6 GB
+        # of a 180 GB part, a third one does not fit  (a `belief` taken from this agent keeps its own reference alive)
+        self._bufs, self._scales = None, None
         if belief is None:
             first = BeliefSet(model, n, device=device)
         else:
