@@ -291,7 +291,8 @@ def run_ours(args) -> None:
     clk = clocks.stop() if rank == 0 else None
     e2e_ms = t2.elapsed_time(t3)
     e2e_steps = int(np.sum(np.where(hist.done_at_step >= 0, hist.done_at_step, len(hist))))
-    d2h = 22.0 * e2e_steps / max(len(hist), 1)                 # int32 action + 2 x int32 position + float64 odor + 2 flag bytes per live agent
+    d2h = 22.0 * n + 16.0                                      # one record buffer per step (float64 odor + 2 x int32 position + int32 action + 2 flag
+                                                               # bytes per agent slot, copied whole) + the 16-byte survivor counts
     h2d = 16.0 * n / max(len(hist), 1)                         # start points (2 x int32) + time shifts (int64), once per run
 
     # ---- second half of the BASELINE metric: PBVI belief-backups/s (C3: B = 10 000 belief points, sharded over the ranks,

@@ -334,18 +334,33 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     counts = torch.zeros(4, dtype=torch.int32, device=dev)
     counts_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
     # two record sets so that step i+1 can run while step i's record is still being copied out
-    recs = [dict(pos=torch.empty((cap, 2), dtype=torch.int32, device=dev), odor=torch.empty(cap, dtype=torch.float64, device=dev),
-                 reached=u8(), term=u8(), act=i32()) for _ in range(2)]
+    # Record sets: ONE contiguous device buffer each (odor f64 | pos 2 x i32 | act i32 | reached u8 | term u8, 22 bytes per agent)
+    # so that a step's record leaves the GPU as a single copy; two device sets (step i + 1 runs while step i's record is copied
+    # out) and three pinned host sets allocated once (the host consumes records two steps late).
+    def record_views(buf):
+        o = 0
+        v = {}
+        for name, dt, shape in (('odor', torch.float64, (cap,)), ('pos', torch.int32, (cap, 2)), ('act', torch.int32, (cap,)),
+                                ('reached', torch.uint8, (cap,)), ('term', torch.uint8, (cap,))):
+            nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size()
+            v[name] = buf[o:o + nbytes].view(dt).view(shape)
+            o += nbytes
+        return v
+    rec_bytes = 22 * cap
+    rec_dev = [torch.empty(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    recs = [record_views(b) for b in rec_dev]
+    rec_host = [torch.empty(rec_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(3)] if record else []
+    rec_host_views = [record_views(b) for b in rec_host]
     rec_free = [None, None]            # event: the record set has been copied out
     pending = []
 
     def flush(upto: int) -> None:
         while len(pending) > upto:
-            ev, (h_act, h_pos, h_odor, h_reached, h_term), m_rec = pending.pop(0)
+            ev, h, m_rec = pending.pop(0)
             ev.synchronize()
-            hist.add_step(actions=h_act.numpy()[:m_rec].astype(np.int64), next_positions=h_pos.numpy()[:m_rec].astype(np.int64),
-                          observations=h_odor.numpy()[:m_rec], reached_source=h_reached.numpy()[:m_rec].astype(bool),
-                          interupt=h_term.numpy()[:m_rec].astype(bool), action_is_id=True)
+            hist.add_step(actions=h['act'].numpy()[:m_rec].astype(np.int64), next_positions=h['pos'].numpy()[:m_rec].astype(np.int64),
+                          observations=h['odor'].numpy()[:m_rec].copy(), reached_source=h['reached'].numpy()[:m_rec].astype(bool),
+                          interupt=h['term'].numpy()[:m_rec].astype(bool), action_is_id=True)
 
     def run_policy(b, scale, rows: int, act_out) -> None:
         'argmax_g b.alpha_g -> action id (agents/pbvi_agent.py:741) or the infotaxis choice (agents/infotaxis_agent.py:244-301).'
@@ -398,7 +413,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         with torch.cuda.device(device):
             check(lib.olfnav_sim_step(model_h, alphas_h, env_h, ctypes.byref(args), stream()))
         counts_host.copy_(counts, non_blocking=True)
-        step_done = torch.cuda.Event()
+        step_done = torch.cuda.Event(blocking=True)        # the host sleeps (not spins) on it: 8 ranks share the host cores
         step_done.record(main)
         if timing is not None:
             evs[4].record(main)
@@ -420,21 +435,15 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 evs += [p0, p1]
 
         # record of this step -> pinned host memory on the side stream
-        bufs = None if not record else (torch.empty(n_live, dtype=torch.int32, pin_memory=True), torch.empty((n_live, 2), dtype=torch.int32, pin_memory=True),
-                torch.empty(n_live, dtype=torch.float64, pin_memory=True), torch.empty(n_live, dtype=torch.uint8, pin_memory=True),
-                torch.empty(n_live, dtype=torch.uint8, pin_memory=True))
-        with torch.cuda.stream(copy_stream) if record else _null_context():
-          if record:
-            copy_stream.wait_event(step_done)
-            bufs[0].copy_(r['act'][:n_live], non_blocking=True)
-            bufs[1].copy_(r['pos'][:n_live], non_blocking=True)
-            bufs[2].copy_(r['odor'][:n_live], non_blocking=True)
-            bufs[3].copy_(r['reached'][:n_live], non_blocking=True)
-            bufs[4].copy_(r['term'][:n_live], non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(copy_stream)
+        if record:
+            flush(2)                                             # the host set about to be overwritten has been consumed
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(step_done)
+                rec_host[i % 3].copy_(rec_dev[i & 1], non_blocking=True)
+                copied = torch.cuda.Event(blocking=True)
+                copied.record(copy_stream)
             rec_free[i & 1] = copied
-            pending.append((copied, bufs, n_live))
+            pending.append((copied, rec_host_views[i % 3], n_live))
         hist._agent_steps = getattr(hist, '_agent_steps', 0) + n_live
 
         step_done.synchronize()                                  # the one host sync of the step
