@@ -323,7 +323,7 @@ def run_ours(args) -> None:
             'e2e': {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'setup_ms_outside_value': setup_ms,
             'clocks': clk,
-            'roofline': {'kernel': 'belief_step_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'roofline': {'kernel': 'belief_step_tma_kernel<256>', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                          # ncu --set full, profiles/r1f_ncu_full_raw_belief_step_and_umma_ts.csv: dram read 12.34 GB + write 12.29 GB per launch
                          # at 99 953 updated rows = 246 442 B per updated agent (algorithmic 246 344 B): scaled to this run's launches
                          'traffic': 246442.0 * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if bs_bytes else None,

@@ -39,6 +39,7 @@ struct StepArgs {
     const float* obs_tab;
     int n;
     int stagger;
+    int rot;               // > 0: CTA i starts its traversal at chunk (i * rot) % nchunks (where the order is free)
     int inplace;
     const int* n_dev;      // optional device-side row count: CTAs with blockIdx.x >= *n_dev exit (grid sized by an upper bound)
 };
@@ -204,10 +205,11 @@ belief_step_kernel(const StepArgs p, const __grid_constant__ Geom g) {
 // E/W shift is a one-element offset of the shared-memory read.  In-place safety is unchanged: a chunk's bulk load
 // completes (mbarrier) before any thread stores that chunk, and later chunks never read rows that earlier chunks
 // wrote (same ordering argument), so prefetching them early is safe.
-constexpr int BS2_THREADS = 256;
+// Two shapes of the same kernel: 256 threads x 16 KB stages x 4 CTAs per SM (grid rows up to ~128 float4: C2's 93), and
+// 512 threads x 32 KB stages x 2 CTAs per SM for wider grids (C5's 186 float4 per row: 11 rows per chunk instead of 5, so the
+// per-CTA stagger below still leaves chunks of >= 8 rows).  Bytes in flight per SM are the same (192 KB).
 constexpr int BS2_UNROLL = 4;
 constexpr int BS2_STAGES = 3;
-constexpr int BS2_STAGE_FLOATS = BS2_THREADS * BS2_UNROLL * 4;     // 16 KB
 
 __device__ __forceinline__ uint32_t bs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -228,8 +230,10 @@ __device__ __forceinline__ void bs_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-__global__ void __launch_bounds__(BS2_THREADS, 4)
+template <int BS2_THREADS>
+__global__ void __launch_bounds__(BS2_THREADS, 1024 / BS2_THREADS)
 belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
+    constexpr int BS2_STAGE_FLOATS = BS2_THREADS * BS2_UNROLL * 4;     // 16 KB (256 threads) or 32 KB (512 threads)
     extern __shared__ __align__(128) float smem[];
     float* stage_base = smem;                                        // BS2_STAGES x BS2_STAGE_FLOATS
     float* halo = smem + BS2_STAGES * BS2_STAGE_FLOATS;              // Wp floats
@@ -254,20 +258,23 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
     // destination rows of the main loop and its chunking (identical to v1)
     int lo_row = 0, hi_row = H;
     if (dy != 0 && !g.wrap_y) { if (dy > 0) hi_row = H - 1; else lo_row = 1; }
-    // Chunk size varies with the CTA index: agents that all take the same action would otherwise run in lockstep
-    // (every CTA loading, then every CTA storing), which costs ~40 % of the HBM bandwidth (measured).
+    // Traversal order.  100 000 agents that all take the same action and all walk their rows in the same order run in
+    // lockstep, and the read and write streams then collide in DRAM: 64-78 % of the HBM bandwidth on uniform actions (measured,
+    // C2 and C5).  Where the order is free (out of place, or dy == 0) CTA i therefore starts at chunk (i * rot) % nchunks and
+    // neighbouring CTAs alternate direction: 97-100 % on every action pattern (profiles/r1j_rot_sweep.jsonl).  In place with
+    // dy != 0 the order is dictated by the move (sources are read before they are overwritten: descending for dy > 0,
+    // ascending for dy < 0); there the chunk SIZE varies with the CTA index instead, which dephases the CTAs over time
+    // (C2 98.6 %, C5 87 %).
     const int rpc_max = max(1, (BS2_THREADS * BS2_UNROLL) / W4);
-    const int rpc = max(1, rpc_max - (p.stagger > 1 ? (int)(blockIdx.x % (unsigned)p.stagger) : 0));
+    const bool free_dir = !p.inplace || dy == 0;
+    const int rpc = max(1, rpc_max - ((!free_dir && p.stagger > 1) ? (int)(blockIdx.x % (unsigned)p.stagger) : 0));
     const int nrows = hi_row - lo_row;
     const int nchunks = (nrows + rpc - 1) / rpc;
-
-    // Traversal direction.  In place it is dictated by the move (sources must be read before they are overwritten):
-    // descending for dy > 0, ascending for dy < 0.  Where it is free (out of place, or dy == 0) neighbouring CTAs
-    // alternate: measured on B200, 100 000 agents all walking the same way reach 65-82 % of the HBM bandwidth, a mix
-    // of ascending and descending streams 99 %.
-    const bool free_dir = !p.inplace || dy == 0;
     const bool desc = free_dir ? ((blockIdx.x & 1u) != 0u) : (dy > 0);
+    const int rot = (free_dir && p.rot > 0 && nchunks > 1) ? (int)(((unsigned)blockIdx.x * (unsigned)p.rot) % (unsigned)nchunks) : 0;
     auto chunk_rows = [&](int k, int& y0, int& y1) {
+        k += rot;
+        if (k >= nchunks) k -= nchunks;
         if (desc) { y1 = hi_row - k * rpc; y0 = max(lo_row, y1 - rpc); }
         else      { y0 = lo_row + k * rpc; y1 = min(hi_row, y0 + rpc); }
     };
@@ -488,18 +495,32 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
     p.ok = ok; p.obs_tab = m->obs; p.n = (int)n;
     static const int stagger = [] { const char* e = getenv("OLFNAV_BELIEF_STAGGER"); return e ? atoi(e) : 4; }();
     p.stagger = stagger;
+    static const int rot = [] { const char* e = getenv("OLFNAV_BELIEF_ROT"); return e ? atoi(e) : 7; }();
+    p.rot = rot;
     p.inplace = inplace ? 1 : 0;
     p.n_dev = n_dev;
-    // v2 (TMA ring) whenever a grid row fits one stage; OLFNAV_BELIEF_V1=1 forces the register-streaming v1 kernel
+    // v2 (TMA ring) whenever a grid row fits one stage; OLFNAV_BELIEF_V1=1 forces the register-streaming v1 kernel.
+    // 256-thread shape (16 KB stages, 4 CTAs per SM) while a grid row fits a stage, 512-thread shape (32 KB stages) for grids wider
+    // than 4096 cells; OLFNAV_BELIEF_THREADS=256|512 overrides the choice (read per call: tests and experiments toggle it).
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_BELIEF_V1"); return e && e[0] == '1'; }();
-    if (!force_v1 && m->g.W4 <= BS2_THREADS * BS2_UNROLL) {
-        const size_t smem2 = (size_t)(BS2_STAGES * BS2_STAGE_FLOATS + m->g.Wp + 40) * sizeof(float) + BS2_STAGES * sizeof(uint64_t);
+    const char* ft = getenv("OLFNAV_BELIEF_THREADS");
+    const int force_threads = ft ? atoi(ft) : 0;
+    auto ring_smem = [&](int threads) {
+        return (size_t)(BS2_STAGES * threads * BS2_UNROLL * 4 + m->g.Wp + 40) * sizeof(float) + BS2_STAGES * sizeof(uint64_t);
+    };
+    const bool fits256 = m->g.W4 <= 256 * BS2_UNROLL && ring_smem(256) <= 56 * 1024;       // 4 CTAs per SM
+    const bool fits512 = m->g.W4 <= 512 * BS2_UNROLL && ring_smem(512) <= 112 * 1024;      // 2 CTAs per SM
+    if (!force_v1 && (fits256 || fits512)) {
+        const int threads = (fits256 && !(force_threads == 512 && fits512)) ? 256 : 512;
+        const size_t smem2 = ring_smem(threads);
         static bool configured = false;
         if (!configured) {
-            OLF_CUDA(cudaFuncSetAttribute(belief_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            OLF_CUDA(cudaFuncSetAttribute(belief_step_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+            OLF_CUDA(cudaFuncSetAttribute(belief_step_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
             configured = true;
         }
-        belief_step_tma_kernel<<<(unsigned)n, BS2_THREADS, smem2, (cudaStream_t)stream>>>(p, m->g);
+        if (threads == 256) belief_step_tma_kernel<256><<<(unsigned)n, 256, smem2, (cudaStream_t)stream>>>(p, m->g);
+        else                belief_step_tma_kernel<512><<<(unsigned)n, 512, smem2, (cudaStream_t)stream>>>(p, m->g);
     } else {
         const size_t smem = (size_t)(m->g.Wp + 40) * sizeof(float);
         if (inplace) belief_step_kernel<true><<<(unsigned)n, BS_THREADS, smem, (cudaStream_t)stream>>>(p, m->g);

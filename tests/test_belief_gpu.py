@@ -56,6 +56,18 @@ def test_golden(cfg, inplace):
     assert np.all(out[~ok] == 0)
 
 
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('inplace', [False, True])
+def test_golden_wide_grid_shape(cfg, inplace, monkeypatch):
+    'The 512-thread / 32 KB-stage shape of the ring kernel (chosen for grids wider than a 16 KB stage) on the same golden vectors.'
+    monkeypatch.setenv('OLFNAV_BELIEF_THREADS', '512')
+    g = golden(f'belief_{cfg}')
+    _, agent = make(cfg)
+    out, ok = _step(agent.model, g['b_in'], g['act'], g['obs'], inplace=inplace)
+    assert np.array_equal(ok, g['ok'])
+    np.testing.assert_allclose(out[ok], g['b_out'][ok], rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize('cfg', ['T0', 'T1', 'T2', 'T3'])
 def test_compacting_and_inplace_row_lists(cfg):
     g = golden(f'belief_{cfg}')
