@@ -108,6 +108,22 @@ int olfnav_belief_step(const olfnav_model* m,
                        uint8_t* ok,                                     /* [dev] n */
                        void* stream);
 
+/* Fused  BeliefSet.update (agents/pbvi_agent.py:783-787)  +  ValueFunction.evaluate_at of the UPDATED beliefs
+ * (agents/pbvi_agent.py:741, the choose_action of the next run_test iteration, simulation.py:1454): one pass over the rows,
+ * 8*S bytes of HBM traffic per agent instead of 12*S.  Same contract as olfnav_belief_step with dst_i = i (b_out != b_in)
+ * followed by olfnav_evaluate(b_out, scale_out): value[i] = max_g b'_i . alpha_g (normalised), arg[i] = first argmax,
+ * action[i] = alpha_actions[arg[i]]; value / arg / action may be NULL.  Needs <= 80 alpha vectors (one tensor-core tile whose partial sums fit the epilogue registers) and
+ * a grid of at least two rows; returns OLFNAV_ERR_UNSUPPORTED otherwise (callers then issue the two calls). */
+int olfnav_can_fuse_policy(const olfnav_model* m, const olfnav_alphas* a);   /* 1: olfnav_belief_step_evaluate supports this pair */
+int olfnav_belief_step_evaluate(const olfnav_model* m, const olfnav_alphas* a,
+                                const float* b_in, float* b_out, int64_t ld, int64_t n,
+                                const int32_t* act, const int32_t* obs,  /* [dev] n */
+                                const int32_t* src_rows,                 /* [dev] n or NULL */
+                                const float* scale_in, float* scale_out, /* [dev] */
+                                uint8_t* ok,                             /* [dev] n */
+                                float* value, int32_t* arg, int32_t* action, /* [dev] n or NULL */
+                                void* stream);
+
 /* Belief compaction — `belief_array[~kill]`, agents/pbvi_agent.py:810-811, agents/infotaxis_agent.py:362-363.
  * dst[i,:] = src[src_rows[i],:] and scale_dst[i] = scale_src[src_rows[i]] for i in [0,n); src != dst. */
 int olfnav_copy_rows(const float* src, float* dst, int64_t ld, int64_t row_len,
@@ -235,6 +251,10 @@ typedef struct olfnav_sim_step_args {
     /* optional cudaEvent_t handles (NULL = none), recorded on `stream`: after the policy kernels, before and after the
      * fused belief update — lets a caller time the dominant kernels live without breaking the single call apart */
     void* ev_policy_end; void* ev_update_begin; void* ev_update_end;
+    /* optional: act_next != NULL (needs alphas != NULL and olfnav_can_fuse_policy(m, alphas) == 1) => the belief update of the
+     * survivors also evaluates the value function on the updated rows (olfnav_belief_step_evaluate) and writes the NEXT step's
+     * action ids of the m survivors to act_next[0..m): the caller skips its own policy call for the next step */
+    int32_t* act_next;
 } olfnav_sim_step_args;
 
 int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas /* NULL = infotaxis */, const olfnav_env* e,

@@ -40,6 +40,8 @@ SIGNATURES = {
     'olfnav_unpack_rows': (_i, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     'olfnav_belief_init': (_i, [_p, _p, _i64, _i64, _p, _p]),
     'olfnav_belief_step': (_i, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'olfnav_belief_step_evaluate': (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'olfnav_can_fuse_policy': (_i, [_p, _p]),
     'olfnav_copy_rows': (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _p]),
     'olfnav_alphas_create': (_i, [ctypes.POINTER(_p), _p, _p, _i64, _p, _i, _p]),
     'olfnav_alphas_destroy': (None, [_p]),
@@ -75,6 +77,7 @@ class SimStepArgs(ctypes.Structure):
         ('rec_pos', _p), ('rec_odor', _p), ('rec_reached', _p), ('rec_term', _p),
         ('counts', _p),
         ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
+        ('act_next', _p),
     ]
 
 

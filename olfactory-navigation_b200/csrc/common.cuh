@@ -136,3 +136,7 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
 // evaluate with caller-provided scratch (val, idx: n entries each); any of value / arg / action may be NULL
 int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n, const float* scale,
                       float* val, int* idx, float* value, int32_t* arg, int32_t* action, int path, cudaStream_t st);
+// fused belief update + evaluation (fused_step.cu); n = upper bound of the rows, n_dev (optional) = exact device-side count
+int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const float* b_in, float* b_out, int64_t ld, int64_t n,
+                          const int32_t* act, const int32_t* obs, const int32_t* src_rows, const float* scale_in, float* scale_out,
+                          uint8_t* ok, float* value, int32_t* arg, int32_t* action, const int* n_dev, cudaStream_t st);

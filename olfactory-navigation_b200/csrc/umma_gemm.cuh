@@ -1,5 +1,6 @@
 // tcgen05 split-precision GEMM with fused segmented max/argmax epilogue (see umma_gemm.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,3 +20,6 @@ int olf_umma_segmax(const float* A, int64_t lda, int64_t n_rows, int K,
 int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K,
                    const float* B_hi, const float* B_lo, int64_t ldb, int rows_b,
                    float* out, int64_t out_ld, int sm_count, cudaStream_t st);
+
+// 2-D tensor map over a row-major FP32 matrix, box = 32 floats x box_rows, 128B swizzle (K-major UMMA operand tiles).
+int olf_make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows);

@@ -302,6 +302,31 @@ class BeliefSet:
             return new, prov
         return new
 
+    def update_and_evaluate(self, value_function: 'ValueFunction', actions, observations, src_rows=None):
+        '''
+        BeliefSet.update followed by ValueFunction.evaluate_at of the updated set (agents/pbvi_agent.py:783-787 then :741) as
+        ONE device pass (olfnav_belief_step_evaluate).  Every row is kept (failed rows: ok False, scale 0).
+        Returns (new BeliefSet, ok bool tensor, values f32, alpha index i32, action i32) — device tensors.
+        '''
+        dev = self._b.device
+        act = torch.as_tensor(np.asarray(actions), dtype=torch.int32, device=dev).contiguous()
+        obs = torch.as_tensor(np.asarray(observations), dtype=torch.int32, device=dev).contiguous()
+        n = int(act.shape[0])
+        rows = None if src_rows is None else torch.as_tensor(np.asarray(src_rows), dtype=torch.int32, device=dev).contiguous()
+        assert obs.shape == (n,) and (rows is not None or n == self._n)
+        out_b = torch.empty((max(n, 1), self._b.shape[1]), dtype=torch.float32, device=dev)
+        out_s = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        ok = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+        val = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        arg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        action = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(self.device):
+            check(lib.olfnav_belief_step_evaluate(self.model.handle(self.device), value_function.handle(self.device), ptr(self._b), ptr(out_b),
+                                                  self.ld, n, ptr(act), ptr(obs), ptr(rows), ptr(self._scale), ptr(out_s), ptr(ok),
+                                                  ptr(val), ptr(arg), ptr(action), stream()))
+        new = BeliefSet(self.model, _buffers=(out_b, out_s, n), device=self.device)
+        return new, ok[:n].bool(), val[:n], arg[:n], action[:n]
+
     def union(self, other: 'BeliefSet') -> 'BeliefSet':
         b = torch.cat([self._b[:self._n], other._b[:other._n]], dim=0)
         s = torch.cat([self._scale[:self._n], other._scale[:other._n]], dim=0)

@@ -1,0 +1,156 @@
+'''
+Fused belief update + value-function evaluation (olfnav_belief_step_evaluate) against the two separate C-ABI calls it
+replaces (olfnav_belief_step then olfnav_evaluate) and against the oracle.
+Bar: updated rows BIT-EXACT with olfnav_belief_step (same arithmetic, same operation order); `ok` flags exact; normalisers
+within 1e-6 relative (different summation order); values within 1e-5 relative; argmax / action indices exact wherever the
+float64 margin between the two best candidates exceeds 1e-5 relative (documented ties below that).
+'''
+import numpy as np
+import pytest
+import torch
+
+from conftest import ALL_CFGS, make, oracle_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_inputs(m, n, G, seed, point_masses=True):
+    rng = np.random.default_rng(seed)
+    d = -np.log(1.0 - rng.random((n, m.state_count)))
+    d[rng.random((n, m.state_count)) < 0.3] = 0.0
+    B = (d / d.sum(1, keepdims=True)).astype(np.float32).astype(np.float64)
+    if point_masses:
+        k = min(12, n)
+        B[:k] = 0
+        B[np.arange(k), rng.integers(0, m.state_count, k)] = 1.0
+    act = rng.integers(0, m.action_count, n)
+    obs = rng.integers(0, m.observation_count - 1, n)
+    alphas = np.abs(rng.standard_normal((G, m.state_count))).astype(np.float32).astype(np.float64)
+    return B, act, obs, alphas, rng.integers(0, m.action_count, G)
+
+
+def _separate(onb, m, vf, bs, act, obs, src_rows=None):
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+    dev = bs._b.device
+    n = len(act)
+    a = torch.as_tensor(act, dtype=torch.int32, device=dev)
+    o = torch.as_tensor(obs, dtype=torch.int32, device=dev)
+    rows = None if src_rows is None else torch.as_tensor(src_rows, dtype=torch.int32, device=dev)
+    out_b = torch.zeros((n, bs._b.shape[1]), dtype=torch.float32, device=dev)
+    out_s = torch.empty(n, dtype=torch.float32, device=dev)
+    ok = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(lib.olfnav_belief_step(m.handle(0), ptr(bs._b), ptr(out_b), bs.ld, n, ptr(a), ptr(o), ptr(rows), None, ptr(bs._scale), ptr(out_s), ptr(ok), stream()))
+    new = onb.BeliefSet(m, _buffers=(out_b, out_s, n), device=0)
+    val, arg, action = vf.evaluate_device(new, 2)
+    return new, ok.bool(), val, arg, action
+
+
+def _compare(new, ok, val, arg, action, ref, vf_actions):
+    rnew, rok, rval, rarg, raction = ref
+    assert torch.equal(ok, rok)
+    assert torch.equal(new._b[:len(ok)], rnew._b[:len(ok)]), 'updated rows must be bit-identical to olfnav_belief_step'
+    good = ok.cpu().numpy()
+    s, rs = new._scale[:len(ok)].cpu().numpy()[good], rnew._scale[:len(ok)].cpu().numpy()[good]
+    np.testing.assert_allclose(s, rs, rtol=1e-6)
+    assert np.all(new._scale[:len(ok)].cpu().numpy()[~good] == 0)
+    # value / argmax against float64 products of the (identical) updated rows
+    rows = rnew.belief_array[good]
+    return rows, good
+
+
+@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('G', [3, 20, 75, 80])
+def test_fused_matches_separate_calls(cfg, G):
+    import olfactory_navigation_b200 as onb
+    _, agent = make(cfg)
+    m = agent.model
+    n = 300
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=G)
+    act[5], obs[6] = 99, -3                                           # invalid ids fail the row
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    bs = onb.BeliefSet(m, B)
+    ref = _separate(onb, m, vf, bs, act, obs)
+    new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
+    rows, good = _compare(new, ok, val, arg, action, ref, alpha_actions)
+    sc = rows @ alphas.T
+    srt = np.sort(sc, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-5 * np.abs(srt[:, -1])
+    np.testing.assert_allclose(val.cpu().numpy()[good], sc.max(1), rtol=1e-5)
+    assert np.array_equal(arg.cpu().numpy()[good][clear], sc.argmax(1)[clear])
+    assert np.array_equal(action.cpu().numpy()[good][clear], alpha_actions[sc.argmax(1)][clear])
+    assert clear.mean() > 0.9
+
+
+@pytest.mark.parametrize('cfg', ['T0', 'T1', 'T2', 'T3'])
+def test_fused_against_oracle(cfg):
+    import olfactory_navigation_b200 as onb
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    _, agent = make(cfg)
+    m, om = agent.model, oracle_model(agent.model)
+    n, G = 200, 9
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=11)
+    new, ok, val, arg, action = onb.BeliefSet(m, B).update_and_evaluate(onb.ValueFunction(m, alphas, alpha_actions), act, obs)
+    ref, prov = tk.BeliefSet(om, B).update(act, obs, raise_on_impossible_belief=False, return_provenance=True)
+    okn = ok.cpu().numpy()
+    assert np.array_equal(np.nonzero(okn)[0], prov[:, 0])
+    np.testing.assert_allclose(new.belief_array[okn], ref.belief_array, rtol=1e-5, atol=1e-30)
+    rv, ra = tk.ValueFunction(om, alphas, alpha_actions).evaluate_at(ref)
+    np.testing.assert_allclose(val.cpu().numpy()[okn], rv, rtol=1e-5)
+    sc = np.sort(ref.belief_array @ alphas.T, axis=1)
+    clear = (sc[:, -1] - sc[:, -2]) > 1e-5 * np.abs(sc[:, -1])
+    assert np.array_equal(action.cpu().numpy()[okn][clear], np.asarray(ra)[clear])
+
+
+@pytest.mark.parametrize('cfg', ['T0', 'T1', 'T3'])
+def test_fused_compacting_row_list(cfg):
+    'src_rows: row i of the output is the update of source row src_rows[i] (the survivors of a simulation step).'
+    import olfactory_navigation_b200 as onb
+    _, agent = make(cfg)
+    m = agent.model
+    n, G = 260, 17
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=5)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    bs = onb.BeliefSet(m, B)
+    rows = np.sort(np.random.default_rng(0).choice(n, 141, replace=False))
+    ref = _separate(onb, m, vf, bs, act[rows], obs[rows], src_rows=rows)
+    new, ok, val, arg, action = bs.update_and_evaluate(vf, act[rows], obs[rows], src_rows=rows)
+    _compare(new, ok, val, arg, action, ref, alpha_actions)
+    np.testing.assert_allclose(val.cpu().numpy(), ref[2].cpu().numpy(), rtol=2e-5)
+
+
+def test_fused_full_size():
+    'BASELINE shape (83x371, wrap_vertical), 1000 agents (7.8 tiles), G = 75, three chained steps.'
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C2')
+    m = agent.model
+    rng = np.random.default_rng(2)
+    n, G = 1000, 75
+    alphas = np.abs(rng.standard_normal((G, m.state_count))).astype(np.float32).astype(np.float64)
+    alpha_actions = rng.integers(0, 4, G)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    bs = onb.BeliefSet(m, n)
+    for step in range(3):
+        act = rng.integers(0, 4, n)
+        obs = (rng.random(n) < 0.2).astype(int)
+        ref = _separate(onb, m, vf, bs, act, obs)
+        new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
+        _compare(new, ok, val, arg, action, ref, alpha_actions)
+        assert bool(ok.all())
+        rv, rarg = ref[2].cpu().numpy(), ref[3].cpu().numpy()
+        np.testing.assert_allclose(val.cpu().numpy(), rv, rtol=1e-5)
+        assert (arg.cpu().numpy() == rarg).mean() > 0.98
+        total = new._b.double().sum(1) * new._scale.double()
+        assert float((total - 1).abs().max()) < 1e-5
+        bs = new
+
+
+def test_unsupported_falls_out_loudly():
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import OlfnavError
+    _, agent = make('T0')
+    m = agent.model
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, 10, 81, seed=1)
+    with pytest.raises(OlfnavError):
+        onb.BeliefSet(m, B).update_and_evaluate(onb.ValueFunction(m, alphas, alpha_actions), act, obs)
