@@ -9,16 +9,27 @@
 //   b'(s') = O(o|s',a) · Σ_s T(s'|s,a) · b(s) · scale          (same arithmetic, same operation order as belief.cu)
 //   action' = actions[argmax_g b' · alpha_g]                    (same 3xTF32 two-level accumulation as umma_gemm.cu)
 //
-// Warp roles (384 threads, one CTA per SM, persistent over tiles of 128 agents):
-//   warp 0      source producer: per agent row, 1-D bulk copies (cp.async.bulk, mbarrier complete_tx) of the 128-float window
-//               of b that feeds the current 128 destination states (shifted by the row's own move: the y-shift is a row-aligned
-//               offset of the copy, wrap-around windows are two copies), +4 floats of halo on both sides for the x-shift
+// Warp roles (640 threads, one CTA per SM, persistent over tiles of 128 agents):
+//   warps 0, 3  source producers: per agent row, 1-D bulk copies (cp.async.bulk, mbarrier complete_tx) of the 128-float window of b
+//               that feeds the current 128 destination states (shifted by the row's own move: the y-shift is a row-aligned offset
+//               of the copy, wrap-around windows are two copies), +4 floats of halo on both sides for the x-shift, plus the chunk's
+//               slice of every likelihood table.  ONE elected lane per warp issues the copies straight-line (~21 cycles each).
 //   warp 1      MMA issuer (tcgen05.mma.kind::tf32, A from tensor memory, B = alpha hi / lo planes from shared memory)
 //   warp 2      TMEM allocator, then TMA producer of the alpha tiles (2-D, 128B swizzle)
-//   warps 4-7   update + transform: thread t owns agent row t of the tile (= TMEM lane t); reads its window from shared memory
-//               (row pitch 140 floats: conflict-free 128-bit reads), applies the x-shift and the boundary rules, multiplies by the
-//               scale and the likelihood, accumulates Z, stores b' to HBM and writes its TF32 hi / lo split to tensor memory
-//   warps 8-11  epilogue: partial accumulators -> FP32 register sums (every 4 k-blocks), first argmax, action lookup
+//   warps 4-11  update + transform, two passes per chunk (see the role's own comment)
+//   warps 12-19 epilogue: partial accumulators -> FP32 register sums every chunk, first argmax per column half, action lookup
+//
+// Status (r1, measured on B200, C2 = 100 000 agents x 30 793 states, G = 75): bit-identical rows, 7.1 ms per step against
+// 6.45 ms for the two separate kernels, so run_test still uses the two kernels (OLFNAV_FUSED_STEP=1 opts in).  What the clock64
+// timeline (OLFNAV_FUSED_DBG=1024) and the ablation bits showed on the way:
+//   * 128 threads arriving on one mbarrier = 128 serialised shared-memory atomics (~500 cycles): arrive once per warp;
+//   * a cp.async.bulk issued by 32 lanes with different operands is an ELECT / R2UR / UBLKCP loop of ~100 cycles per copy;
+//     one elected lane issues a copy per ~21 cycles, and the SM's copy engine retires ~one 512-byte copy per 22 cycles whatever
+//     the number of issuing threads (loads and stores together): b' therefore leaves through coalesced st.global, not bulk stores;
+//   * with 227 KB of shared memory the L1 is too small for local memory: every spill or dynamically indexed array is an L2 round trip;
+//   * the update pass is instruction-issue bound (~95 SASS instructions per 512-byte row visit, 3x the stand-alone belief kernel);
+//   * TMA tensor copies cannot do the x-shift: the innermost start coordinate must be 16-byte aligned (scripts/tma_row_test.cu:
+//     columns -24 and 4 work, -25 and 1 raise "illegal instruction").
 #include "common.cuh"
 #include "stencil.cuh"
 #include "umma_gemm.cuh"

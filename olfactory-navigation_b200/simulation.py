@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from datetime import datetime
 
+import os
+
 import numpy as np
 import torch
 
@@ -372,6 +374,10 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                                           int(getattr(agent, 'gemm_path', 0)), stream()))
 
     args = SimStepArgs()
+    # OLFNAV_FUSED_STEP=1: the belief update of a step also evaluates the value function on the updated rows (one pass over the
+    # beliefs, olfnav_belief_step_evaluate) and delivers the next step's actions.  Opt-in: bit-identical rows, not yet faster (r1).
+    fused = (not is_infotaxis and os.environ.get('OLFNAV_FUSED_STEP', '0') == '1'
+             and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
     n_live, cur = n, 0
     have_act = False                   # the next step's actions were computed ahead of time (see the end of the loop body)
     iterator = range(horizon)
@@ -404,6 +410,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
         args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
         args.counts = counts.data_ptr()
+        args.act_next = recs[(i + 1) & 1]['act'].data_ptr() if (fused and i + 1 < horizon) else None
+        if fused and i + 1 < horizon and rec_free[(i + 1) & 1] is not None:
+            main.wait_event(rec_free[(i + 1) & 1])             # the next record set receives its actions during this step
         if timing is not None:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             for e in evs:
@@ -429,7 +438,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             if timing is not None:
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record(main)
-            run_policy(b_nxt, s_nxt, n_live, nxt['act'])
+            if not fused:
+                run_policy(b_nxt, s_nxt, n_live, nxt['act'])
             if timing is not None:
                 p1.record(main)
                 evs += [p0, p1]
