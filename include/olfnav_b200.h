@@ -203,6 +203,10 @@ int olfnav_vi_sweep(const olfnav_model* m, const double* Q_in, double* Q_out, in
 int  olfnav_env_create(olfnav_env** out, int device, int H, int W, int boundary,
                        const double* data, int T, int h, int w, int margin_y, int margin_x,
                        double source_y, double source_x, double source_radius);
+/* Layered data (environment.py:202-235): data [host] L x T x h x w; olfnav_sim_step picks the layer of each agent's action. */
+int  olfnav_env_create_layered(olfnav_env** out, int device, int H, int W, int boundary,
+                               const double* data, int L, int T, int h, int w, int margin_y, int margin_x,
+                               double source_y, double source_x, double source_radius);
 void olfnav_env_destroy(olfnav_env* e);
 
 /* One simulation step for n agents (simulation.py:1457-1466 + agent.py:401-439):
@@ -255,6 +259,9 @@ typedef struct olfnav_sim_step_args {
      * survivors also evaluates the value function on the updated rows (olfnav_belief_step_evaluate) and writes the NEXT step's
      * action ids of the m survivors to act_next[0..m): the caller skips its own policy call for the next step */
     int32_t* act_next;
+    /* layered environments (environment.py:202-235; simulation.py:1456-1463): layer of every action id (A ints, NULL without
+     * layers), thresholds laid out [L][n_thr] when thr_per_layer = 1 (agent.py:414-417), L + 1 ints of scratch for time_mode 1 */
+    const int32_t* act_layer; int32_t thr_per_layer; int32_t* hist_layer;
 } olfnav_sim_step_args;
 
 int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas /* NULL = infotaxis */, const olfnav_env* e,

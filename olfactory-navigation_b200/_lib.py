@@ -53,6 +53,7 @@ SIGNATURES = {
     'olfnav_backup_assemble': (_i, [_p, _p, _i64, _i, _p, _p, _i64, _p, _i64, _p]),
     'olfnav_vi_sweep': (_i, [_p, _p, _p, _i64, _d, _p, _p]),
     'olfnav_env_create': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _d, _d, _d]),
+    'olfnav_env_create_layered': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _d, _d, _d]),
     'olfnav_env_destroy': (None, [_p]),
     'olfnav_env_step': (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i, _p, _p, _p, _p]),
 }
@@ -78,6 +79,7 @@ class SimStepArgs(ctypes.Structure):
         ('counts', _p),
         ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
         ('act_next', _p),
+        ('act_layer', _p), ('thr_per_layer', ctypes.c_int32), ('hist_layer', _p),
     ]
 
 

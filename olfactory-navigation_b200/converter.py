@@ -18,25 +18,34 @@ from .pomdp import POMDP
 def exact_converter(agent) -> POMDP:
     env = agent.environment
     thr = agent.thresholds
-    moves = np.asarray(agent.action_set)
+    action_set = np.asarray(agent.action_set)
+    moves = action_set[:, 1:] if env.has_layers else action_set          # the physical part of a layered action (:113)
     assert env.dimensions == 2, 'This converter only works for 2D environments...'
-    assert not agent.space_aware, 'This model is not compatible with space_aware agents'
+    assert not agent.space_aware, 'This model is not compatible with space_aware agents as the observations would not match the expected observations of this model.'
     H, W = env.shape
-    S, A, O = H * W, len(moves), len(thr)          # bins (= len(thr) - 1) + goal
+    S, A, O = H * W, len(moves), thr.shape[-1]          # bins (= len(thr) - 1) + goal
 
     yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
     end_mask = (((yy - env.source_position[0]) ** 2 + (xx - env.source_position[1]) ** 2) <= env.source_radius ** 2).ravel()
     end_states = np.flatnonzero(end_mask).tolist()
 
-    # time-averaged probability of each odor bin inside the data zone
-    data = env.data[:, :, :, None]
-    in_bin = (data >= thr[:-1][None, None, None, :]) & (data < thr[1:][None, None, None, :])
-    fields = np.zeros((H, W, O - 1))
+    # time-averaged probability of each odor bin inside the data zone (one field per layer, thresholds possibly per layer, :54-65)
     (y0, y1), (x0, x1) = env.data_bounds
-    fields[y0:y1, x0:x1, :] = np.average(in_bin, axis=0)
+
+    def field(frames, t):
+        data = frames[:, :, :, None]
+        in_bin = (data >= t[:-1][None, None, None, :]) & (data < t[1:][None, None, None, :])
+        f = np.zeros((H, W, O - 1))
+        f[y0:y1, x0:x1, :] = np.average(in_bin, axis=0)
+        return f
 
     obs = np.empty((S, A, O))
-    obs[:, :, :O - 1] = fields.reshape(S, 1, O - 1)
+    if env.has_layers:
+        fields = [field(env.data[layer], thr[layer] if thr.ndim == 2 else thr) for layer in env.layers]
+        for a in range(A):
+            obs[:, a, :O - 1] = fields[int(action_set[a, 0])].reshape(S, O - 1)
+    else:
+        obs[:, :, :O - 1] = field(env.data, thr).reshape(S, 1, O - 1)
     margin = np.ones((H, W), dtype=bool)
     margin[y0:y1, x0:x1] = False
     obs[margin.ravel(), :, 0] = 1.0

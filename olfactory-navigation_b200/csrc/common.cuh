@@ -82,8 +82,9 @@ struct olfnav_env {
     int device;
     int H, W, wrap_y, wrap_x;
     int T, h, w, my, mx;
+    int L;             // layers (1 without layers)
     double sy, sx, r2;
-    double* data;      // [T][h][w]
+    double* data;      // [L][T][h][w]
 };
 
 // ---- small device helpers ----------------------------------------------------------------------------

@@ -180,11 +180,11 @@ extern "C" int olfnav_model_dims(const olfnav_model* m, int* H, int* W, int* Wp,
 }
 
 // ------------------------------------------------------------------------------------------------------
-extern "C" int olfnav_env_create(olfnav_env** out, int device, int H, int W, int boundary,
-                                 const double* data, int T, int h, int w, int margin_y, int margin_x,
-                                 double source_y, double source_x, double source_radius) {
+extern "C" int olfnav_env_create_layered(olfnav_env** out, int device, int H, int W, int boundary,
+                                         const double* data, int L, int T, int h, int w, int margin_y, int margin_x,
+                                         double source_y, double source_x, double source_radius) {
     OLF_REQUIRE(out && data, "env_create: null argument");
-    OLF_REQUIRE(H >= 1 && W >= 1 && T >= 1 && h >= 1 && w >= 1, "env_create: bad sizes");
+    OLF_REQUIRE(H >= 1 && W >= 1 && L >= 1 && T >= 1 && h >= 1 && w >= 1, "env_create: bad sizes");
     int wy, wx;
     OLF_REQUIRE(set_boundary(boundary, &wy, &wx) == 0, "env_create: unknown boundary %d", boundary);
     OLF_CUDA(cudaSetDevice(device));
@@ -192,9 +192,9 @@ extern "C" int olfnav_env_create(olfnav_env** out, int device, int H, int W, int
     if (!e) { olfnav_set_error("env_create: out of host memory"); return OLFNAV_ERR_NOMEM; }
     memset(e, 0, sizeof(*e));
     e->device = device; e->H = H; e->W = W; e->wrap_y = wy; e->wrap_x = wx;
-    e->T = T; e->h = h; e->w = w; e->my = margin_y; e->mx = margin_x;
+    e->L = L; e->T = T; e->h = h; e->w = w; e->my = margin_y; e->mx = margin_x;
     e->sy = source_y; e->sx = source_x; e->r2 = source_radius * source_radius;
-    const size_t bytes = (size_t)T * h * w * sizeof(double);
+    const size_t bytes = (size_t)L * T * h * w * sizeof(double);
     cudaError_t ce = cudaMalloc((void**)&e->data, bytes);
     if (ce == cudaSuccess) ce = cudaMemcpy(e->data, data, bytes, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
@@ -204,6 +204,12 @@ extern "C" int olfnav_env_create(olfnav_env** out, int device, int H, int W, int
     }
     *out = e;
     return OLFNAV_OK;
+}
+
+extern "C" int olfnav_env_create(olfnav_env** out, int device, int H, int W, int boundary,
+                                 const double* data, int T, int h, int w, int margin_y, int margin_x,
+                                 double source_y, double source_x, double source_radius) {
+    return olfnav_env_create_layered(out, device, H, W, boundary, data, 1, T, h, w, margin_y, margin_x, source_y, source_x, source_radius);
 }
 
 extern "C" void olfnav_env_destroy(olfnav_env* e) {

@@ -57,7 +57,15 @@ __global__ void time_scan_kernel(int T, int* __restrict__ hist) {
     }
 }
 
+// layer histogram for the reference's sorted-layer indexing (same quirk as for the times, environment.py:594-595)
+__global__ void layer_hist_kernel(int n, const int* __restrict__ act, const int* __restrict__ act_layer, int* __restrict__ hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&hist[act_layer[act[i]] + 1], 1);
+}
+
 struct EnvArgs {
+    const int* act_layer; const int* hist_layer; int thr_per_layer;
     int n;
     const int* pos_in; const int* act; const int* moves; const long long* ts; long long step;
     const double* thr; int n_thr; const int* hist; int time_mode; int time_loop;
@@ -82,15 +90,25 @@ __global__ void sim_env_kernel(const olfnav_env e, const EnvArgs a) {
         t = (a.ts[i] + a.step) % e.T;
         if (t < 0) t += e.T;
     }
+    // layered environment: the layer is the first component of the action (simulation.py:1461-1463); under the reference's
+    // indexing quirk agent i observes the i-th smallest layer
+    const int own_layer = a.act_layer ? a.act_layer[act] : 0;
+    int layer = own_layer;
+    if (a.act_layer && a.time_mode == 1) {
+        int lo = 0, hi = e.L - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.hist_layer[mid] <= i) lo = mid; else hi = mid - 1; }
+        layer = lo;
+    }
     const int dyp = y - e.my, dxp = x - e.mx;
     double v = 0.0;
-    if (dyp >= 0 && dyp < e.h && dxp >= 0 && dxp < e.w) v = e.data[((size_t)t * e.h + dyp) * e.w + dxp];
+    if (dyp >= 0 && dyp < e.h && dxp >= 0 && dxp < e.w) v = e.data[(((size_t)layer * e.T + t) * e.h + dyp) * e.w + dxp];
     a.rec_odor[i] = v;
     const double ddy = (double)y - e.sy, ddx = (double)x - e.sx;
     const bool hit = (ddy * ddy + ddx * ddx) <= e.r2;
     int id = -1;
+    const double* thr = a.thr + (a.thr_per_layer ? (size_t)own_layer * a.n_thr : 0);      // per-layer thresholds (agent.py:414-417)
     for (int k = 0; k + 1 < a.n_thr; ++k)
-        if (v >= a.thr[k] && v < a.thr[k + 1]) { id = k; break; }
+        if (v >= thr[k] && v < thr[k + 1]) { id = k; break; }
     a.obs_id[i] = hit ? (a.n_thr - 1) : id;
     a.rec_reached[i] = hit ? 1 : 0;
     a.rec_term[i] = hit ? 1 : 0;
@@ -194,7 +212,16 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
         time_scan_kernel<<<1, 1024, 0, st>>>(e->T, a->hist);
         olf_count_launch(2);
     }
+    OLF_REQUIRE(e->L == 1 || a->act_layer, "sim_step: a layered environment needs act_layer (layer of every action id)");
+    OLF_REQUIRE(!(a->act_layer && a->time_mode == 1) || a->hist_layer, "sim_step: time_mode 1 with layers needs the hist_layer scratch (L + 1 ints)");
+    if (a->act_layer && a->time_mode == 1) {
+        OLF_CUDA(cudaMemsetAsync(a->hist_layer, 0, (size_t)(e->L + 1) * sizeof(int), st));
+        layer_hist_kernel<<<grid, 256, 0, st>>>(n, a->act, a->act_layer, a->hist_layer);
+        time_scan_kernel<<<1, 1024, 0, st>>>(e->L, a->hist_layer);
+        olf_count_launch(2);
+    }
     EnvArgs ea;
+    ea.act_layer = a->act_layer; ea.hist_layer = a->hist_layer; ea.thr_per_layer = a->thr_per_layer;
     ea.n = n; ea.pos_in = a->pos_in; ea.act = a->act; ea.moves = a->moves; ea.ts = (const long long*)a->ts_in; ea.step = (long long)a->step;
     ea.thr = a->thresholds; ea.n_thr = a->n_thr; ea.hist = a->hist; ea.time_mode = a->time_mode; ea.time_loop = a->time_loop;
     ea.rec_pos = a->rec_pos; ea.rec_odor = a->rec_odor; ea.obs_id = a->obs_id; ea.rec_reached = a->rec_reached; ea.rec_term = a->rec_term;

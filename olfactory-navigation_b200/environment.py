@@ -8,7 +8,7 @@ geometry (margins / shape / data bounds / source, :277-377), start probabilities
 reference exposes and are what `exact_converter` uses to build the move table.
 
 shape= / multiplier= resampling, save / load and modify / modify_scale are host-side one-offs kept in
-NumPy / SciPy.  Out of scope (raise NotImplementedError): h5 files, layers, `shape=` /
+NumPy / SciPy.  Layered data (layer, time, y, x) is supported.  Out of scope (raise NotImplementedError): h5 files, `shape=` /
 `multiplier=` resampling, save/load, plotting, modify()/modify_scale().
 '''
 from __future__ import annotations
@@ -49,8 +49,8 @@ class Environment:
                  start_zone: str | np.ndarray = 'data_zone',
                  odor_present_threshold: float = None,
                  name: str = None) -> None:
-        if layers not in (False, None):
-            raise NotImplementedError('layered environments are out of scope of the B200 hot path (SURVEY §8 f4)')
+        # layers (environment.py:202-235): data of shape (layer, time, y, x); a list names the layers
+        has_layers = isinstance(layers, (list, tuple)) or layers is True
 
         if isinstance(data_file, str):
             if not data_file.endswith('.npy'):
@@ -62,15 +62,22 @@ class Environment:
             data = data_file
         else:
             raise NotImplementedError('data_file must be a .npy path or a numpy array')
-        assert data.ndim == 3, 'data must have shape (time, y, x)'
+        assert data.ndim == (4 if has_layers else 3), 'data must have shape (time, y, x), or (layer, time, y, x) with layers'
 
         self._data = np.ascontiguousarray(data, dtype=np.float64)
         self._original_data = self._data
         self._preprocess_data = preprocess_data
         self.saved_at = None
-        self.layers, self.layer_labels, self.has_layers = None, None, False
-        self.timesteps = int(self._data.shape[0])
-        self.data_shape = tuple(int(v) for v in self._data.shape[1:])
+        self.layers, self.layer_labels, self.has_layers = None, None, has_layers
+        if has_layers:
+            self.layers = np.arange(len(self._data))
+            if isinstance(layers, (list, tuple)):
+                assert len(layers) == len(self._data), 'The amount of layers provided dont match the amount in the dataset.'
+                self.layer_labels = [str(layer) for layer in layers]
+            else:
+                self.layer_labels = [str(layer) for layer in range(len(self._data))]
+        self.timesteps = int(self._data.shape[-3])
+        self.data_shape = tuple(int(v) for v in self._data.shape[-2:])
         self.dimensions = 2
         self.data_source_position = np.array(data_source_position)
         self.original_data_source_position = self.data_source_position
@@ -117,7 +124,9 @@ class Environment:
         self.data_source_position = new_source
         self.data_shape = tuple(int(v) for v in scaled_shape)
         if self.data_shape != original_data_shape:
-            self._data = np.stack([_resize_array(frame, self.data_shape, interpolation_method.lower()) for frame in self._data])
+            frames = self._data.reshape((-1,) + self._data.shape[-2:])
+            frames = np.stack([_resize_array(frame, self.data_shape, interpolation_method.lower()) for frame in frames])
+            self._data = frames.reshape(self._data.shape[:-2] + self.data_shape)
         self.data_processed = True
 
         self.shape = tuple(int(d + lo + hi) for d, (lo, hi) in zip(self.data_shape, self.margins))
@@ -146,12 +155,13 @@ class Environment:
             probs[inner] = 1.0
         elif start_zone == 'odor_present':
             thr = 0 if odor_present_threshold is None else odor_present_threshold
+            frames0 = self._data[0] if self.has_layers else self._data       # layered: the first layer decides (environment.py:408)
             if self.data_shape != original_data_shape and not preprocess_data:
                 # reference quirk (environment.py:402-413): on lazily resampled data the map is the FRACTION of frames with odor,
                 # not the 0/1 indicator used for data that is already at its final shape
-                probs[inner] = np.mean((self._data > thr).astype(float), axis=0)
+                probs[inner] = np.mean((frames0 > thr).astype(float), axis=0)
             else:
-                probs[inner] = (np.mean((self._data > thr).astype(int), axis=0) > 0).astype(float)
+                probs[inner] = (np.mean((frames0 > thr).astype(int), axis=0) > 0).astype(float)
         else:
             raise ValueError('start_zone value is wrong')
         self.odor_present_threshold = odor_present_threshold
@@ -196,7 +206,7 @@ class Environment:
 
     # -- per-step host API (NumPy) ---------------------------------------------------------------
     def get_observation(self, pos: np.ndarray, time: int | np.ndarray = 0, layer: int | np.ndarray = 0):
-        'data[time % T, pos - low margins], 0.0 outside the data zone (environment.py:554-652).'
+        'data[(layer,) time % T, pos - low margins], 0.0 outside the data zone (environment.py:554-652).'
         pos = np.asarray(pos)
         single = pos.ndim == 1
         p = pos[None, :] if single else pos
@@ -206,7 +216,13 @@ class Environment:
         dp = p - self.margins[:, 0][None, :]
         inside = np.all((dp >= 0) & (dp < np.array(self.data_shape)[None, :]), axis=1)
         out = np.zeros(len(p), dtype=float)
-        out[inside] = self._data[t[inside], dp[inside, 0], dp[inside, 1]]
+        if self.has_layers:
+            lay = np.broadcast_to(np.asarray(layer), (len(p),))
+            if self.reference_time_quirk and np.ndim(layer) > 0:
+                lay = np.sort(lay)             # same indexing quirk as for the times (environment.py:594-595,645)
+            out[inside] = self._data[lay[inside], t[inside], dp[inside, 0], dp[inside, 1]]
+        else:
+            out[inside] = self._data[t[inside], dp[inside, 0], dp[inside, 1]]
         return float(out[0]) if single else out
 
     def source_reached(self, pos: np.ndarray):
@@ -272,7 +288,7 @@ class Environment:
         arguments.update(timesteps=int(self.timesteps), data_shape=list(self.data_shape), dimensions=self.dimensions,
                          margins=self.margins.tolist(), shape=list(self.shape), data_bounds=self.data_bounds.tolist(),
                          original_data_source_position=np.asarray(self.original_data_source_position).tolist(),
-                         data_source_position=self.data_source_position.tolist(), layers=False,
+                         data_source_position=self.data_source_position.tolist(), layers=(self.layer_labels if self.has_layers else False),
                          source_position=self.source_position.tolist(), source_radius=self.source_radius,
                          interpolation_method=self.interpolation_method, preprocess_data=self._preprocess_data,
                          data_processed=self.data_processed, boundary_condition=self.boundary_condition, start_type=self.start_type)
@@ -303,7 +319,9 @@ class Environment:
             env.original_data_source_position = np.array(a['original_data_source_position'])
             env.data_source_position, env.source_position = np.array(a['data_source_position']), np.array(a['source_position'])
             env.source_radius = a['source_radius']
-            env.has_layers, env.layers, env.layer_labels = False, None, None
+            env.has_layers = bool(a.get('layers'))
+            env.layers = np.arange(len(env._data)) if env.has_layers else None
+            env.layer_labels = list(a['layers']) if env.has_layers else None
             env.interpolation_method, env._preprocess_data, env.data_processed = a['interpolation_method'], a['preprocess_data'], True
             env.boundary_condition = a['boundary_condition']
             env.data_file_path, env.odor_present_threshold, env.start_type = a.get('data_file_path'), a.get('odor_present_threshold'), a.get('start_type')
@@ -331,7 +349,7 @@ class Environment:
         return Environment(data_file=self._source_data(),
                            data_source_position=(data_source_position if data_source_position is not None else self.original_data_source_position),
                            source_radius=(source_radius if source_radius is not None else self.source_radius),
-                           layers=False,
+                           layers=(self.layer_labels if self.has_layers else False),
                            shape=(shape if shape is not None else self.shape),
                            margins=(margins if margins is not None else self.margins),
                            multiplier=(multiplier if multiplier is not None else [1.0, 1.0]),
@@ -343,7 +361,7 @@ class Environment:
     def modify_scale(self, scale_factor: float) -> 'Environment':
         'Everything scaled by one factor: shape, margins, source radius and data shape (environment.py:1126-1161).'
         return Environment(data_file=self._source_data(), data_source_position=self.original_data_source_position,
-                           source_radius=self.source_radius * scale_factor, layers=False,
+                           source_radius=self.source_radius * scale_factor, layers=(self.layer_labels if self.has_layers else False),
                            shape=(np.array(self.shape) * scale_factor).astype(int),
                            margins=(self.margins * scale_factor).astype(int), multiplier=[1.0, 1.0],
                            interpolation_method=self.interpolation_method, preprocess_data=self._preprocess_data,
@@ -357,12 +375,13 @@ class Environment:
             from . import _lib
             _lib.require_cuda()
             h = ctypes.c_void_p()
-            T, dh, dw = self._data.shape
-            _lib.check(_lib.lib.olfnav_env_create(ctypes.byref(h), device, self.shape[0], self.shape[1],
-                                                  _lib.BOUNDARY.get(self.boundary_condition, 0), _lib.ptr(self._data), T, dh, dw,
-                                                  int(self.margins[0, 0]), int(self.margins[1, 0]),
-                                                  float(self.source_position[0]), float(self.source_position[1]),
-                                                  float(self.source_radius)))
+            T, dh, dw = self._data.shape[-3:]
+            L = len(self.layers) if self.has_layers else 1
+            _lib.check(_lib.lib.olfnav_env_create_layered(ctypes.byref(h), device, self.shape[0], self.shape[1],
+                                                          _lib.BOUNDARY.get(self.boundary_condition, 0), _lib.ptr(self._data), L, T, dh, dw,
+                                                          int(self.margins[0, 0]), int(self.margins[1, 0]),
+                                                          float(self.source_position[0]), float(self.source_position[1]),
+                                                          float(self.source_radius)))
             self._device_handles[device] = _EnvHandle(h)
         return self._device_handles[device].h
 

@@ -321,7 +321,10 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     ts = [torch.as_tensor(np.ascontiguousarray(time_shift), dtype=torch.int64, device=dev).contiguous() if n else torch.zeros(1, dtype=torch.int64, device=dev),
           torch.empty(cap, dtype=torch.int64, device=dev)]
     thresholds = torch.as_tensor(agent.thresholds, dtype=torch.float64, device=dev).contiguous()
-    moves = torch.as_tensor(np.ascontiguousarray(agent.action_set), dtype=torch.int32, device=dev).contiguous()
+    moves = torch.as_tensor(np.ascontiguousarray(agent.movement_set), dtype=torch.int32, device=dev).contiguous()
+    layered = bool(environment.has_layers)
+    act_layer = torch.as_tensor(np.ascontiguousarray(agent.action_layers), dtype=torch.int32, device=dev).contiguous() if layered else None
+    hist_layer = torch.zeros(len(environment.layers) + 1, dtype=torch.int32, device=dev) if layered else None
     T = environment.timesteps
 
     def i32(k=cap):
@@ -400,7 +403,10 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.pos_in, args.pos_out = pos[cur].data_ptr(), pos[1 - cur].data_ptr()
         args.ts_in, args.ts_out = ts[cur].data_ptr(), ts[1 - cur].data_ptr()
         args.n, args.step = n_live, i
-        args.moves, args.thresholds, args.n_thr = moves.data_ptr(), thresholds.data_ptr(), int(thresholds.numel())
+        args.moves, args.thresholds, args.n_thr = moves.data_ptr(), thresholds.data_ptr(), int(thresholds.shape[-1])
+        args.act_layer = act_layer.data_ptr() if layered else None
+        args.hist_layer = hist_layer.data_ptr() if layered else None
+        args.thr_per_layer = 1 if thresholds.dim() == 2 else 0
         args.time_mode = 1 if environment.reference_time_quirk else 0
         args.time_loop = 1 if time_loop else 0
         args.eval_path = int(getattr(agent, 'gemm_path', 0))
@@ -505,9 +511,11 @@ def _run_generic(agent, n, start_points, time_shift, environment, time_loop, hor
                              horizon=horizon, reward_discount=reward_discount, distance_metric=distance_metric, used_gpu=False)
     for i in range(horizon):
         action = agent.choose_action()
-        pos = environment.move(pos=pos, movement=action)
-        observation = environment.get_observation(pos=pos, time=(ts + i))
+        pos = environment.move(pos=pos, movement=(action if not environment.has_layers else action[:, 1:]))
+        observation = environment.get_observation(pos=pos, time=(ts + i), layer=(0 if not environment.has_layers else action[:, 0]))
         reached = environment.source_reached(pos)
+        if agent.space_aware:
+            observation = np.hstack((observation[:, None], pos))
         ok = agent.update_state(action=action, observation=observation, source_reached=reached)
         if ok is None:
             ok = np.ones(len(reached), dtype=bool)

@@ -59,3 +59,18 @@ def config(name: str) -> dict:
                   start_zone=c['start_zone'],
                   odor_present_threshold=(0.0 if c['start_zone'] == 'odor_present' else None))
     return dict(env_kwargs=kwargs, thresholds=c['thresholds'])
+
+
+def layered_config(name: str = 'L1') -> dict:
+    '''
+    A tiny LAYERED environment (reference environment.py:202-235): two layers over the T1 geometry — a narrow plume
+    ("ground") and a wider, weaker one ("air").  thresholds: shared by the layers; thresholds_per_layer: one row per layer.
+    '''
+    assert name == 'L1'
+    c = CONFIGS['T1']
+    ground = plume_frames(c['T'], c['h'], c['w'], source_y=c['source'][0], seed=SEED)
+    air = plume_frames(c['T'], c['h'], c['w'], source_y=c['source'][0], seed=SEED + 7, p0=0.7, sigma0=2.0, k=0.8)
+    kwargs = dict(data_file=np.stack([ground, air]), data_source_position=list(c['source']), source_radius=c['radius'],
+                  layers=['ground', 'air'], margins=list(c['margins']), boundary_condition=c['boundary'],
+                  start_zone='data_zone')        # 'odor_present' breaks the reference's constructor on layered arrays (environment.py:404)
+    return dict(env_kwargs=kwargs, thresholds=[0.3, 0.6], thresholds_per_layer=np.array([[0.3, 0.6], [0.2, 0.5]]))

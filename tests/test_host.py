@@ -58,8 +58,16 @@ def test_agent_constructor_variants():
     assert ag.action_set.tolist() == [[-1, 0], [0, 0]] and ag.action_labels == ['N', 'stay']
     ag = onb.agents.PBVI_Agent(env, thresholds=0.5, spatial_subdivisions=[2, 2], rng=3)    # stray kwarg swallowed like the reference
     assert ag.model.state_count == env.shape[0] * env.shape[1]
-    with pytest.raises(NotImplementedError):
-        onb.Agent(env, space_aware=True)
+    # space-aware observations (reference agent.py:206-234,418-434): odor bin x position cell, goal id = bins x cells
+    sa = onb.Agent(env, thresholds=0.5, space_aware=True, spacial_subdivisions=[2, 3])
+    H, W = env.shape
+    obs = np.array([[0.9, 0, 0], [0.1, H - 1, W - 1], [0.9, H - 1, 0], [0.3, 5, 5]], dtype=float)
+    ids = sa.discretize_observations(obs, None, np.array([False, False, False, True]))
+    cells = sa._environment_to_subdivision_mapping
+    assert cells.min() == 0 and cells.max() == 5
+    assert ids.tolist() == [1 * 6 + cells[0, 0], 0 * 6 + cells[H - 1, W - 1], 1 * 6 + cells[H - 1, 0], 2 * 6]
+    with pytest.raises(AssertionError):             # the converters reject space-aware agents like the reference's (environment_converter.py:37)
+        onb.agents.PBVI_Agent(env, thresholds=0.5, space_aware=True)
 
 
 def test_random_start_points_rng_stream():
