@@ -76,6 +76,15 @@ uint64_t    olfnav_kernel_launches(void);               /* kernels this library 
 int  olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O,
                          const int32_t* moves, int boundary,
                          const double* obs_table, const uint8_t* end_mask, const double* start);
+/* Dense stochastic-transition model — POMDP(states, actions, observations, transition_table = T[s, a, s'], observation_table,
+ * end_states, start_probabilities) as built by the reference's minimal_converter
+ * (agents/model_based_util/environment_converter.py:137-292, call :282-290).  Every entry point that takes an olfnav_model
+ * (belief step, evaluate, backup, VI sweep, infotaxis, sim step) accepts it; the state space is a flat list (H = 1, W = S). */
+int olfnav_model_create_dense(olfnav_model** out, int device, int S, int A, int O,
+                              const double* transition_table,   /* [host] S x A x S */
+                              const double* obs_table,          /* [host] S x A x O */
+                              const uint8_t* end_mask,          /* [host] S */
+                              const double* start);             /* [host] S */
 void olfnav_model_destroy(olfnav_model* m);
 int  olfnav_model_dims(const olfnav_model* m, int* H, int* W, int* Wp, int* A, int* O);
 

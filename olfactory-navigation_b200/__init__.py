@@ -17,6 +17,6 @@ from .agent import Agent                              # noqa: F401
 from .pomdp import POMDP, Belief, BeliefSet, ValueFunction   # noqa: F401
 from . import solvers                                 # noqa: F401
 from . import agents                                  # noqa: F401
-from .converter import exact_converter                # noqa: F401
+from .converter import exact_converter, minimal_converter   # noqa: F401
 from .simulation import run_test, SimulationHistory   # noqa: F401
 from . import synthetic                               # noqa: F401

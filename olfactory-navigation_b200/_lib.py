@@ -39,6 +39,7 @@ SIGNATURES = {
     'olfnav_pack_rows': (_i, [_p, _p, _p, _p, _i64, _i64, _p]),
     'olfnav_unpack_rows': (_i, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     'olfnav_belief_init': (_i, [_p, _p, _i64, _i64, _p, _p]),
+    'olfnav_model_create_dense': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _p, _p, _p]),
     'olfnav_belief_step': (_i, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     'olfnav_belief_step_evaluate': (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'olfnav_can_fuse_policy': (_i, [_p, _p]),

@@ -65,3 +65,88 @@ def exact_converter(agent) -> POMDP:
                  start_probabilities=env.start_probabilities.ravel(),
                  grid_shape=(H, W), moves=moves,
                  boundary=('stop' if env.boundary_condition == 'clip' else env.boundary_condition))
+
+
+def minimal_converter(agent, partitions=[3, 6], margin_partitions: bool = False) -> POMDP:
+    '''
+    A handful of partition cells + one goal state with stochastic transitions between them — same tables as the reference's
+    minimal_converter (reference agents/model_based_util/environment_converter.py:137-292):
+      * cells: `partitions` (y, x) cells over the data zone plus one ring of margin cells per axis (margin_partitions=True), or over
+        the whole grid (False; that branch of the reference cannot run: its observation block reshapes to partitions + 2, :264);
+      * T[cell, a, cell'] = fraction of the cell's grid points that environment.move sends into cell' without reaching the source,
+        T[cell, a, goal] = fraction that reaches it; the goal state is absorbing (:207-224);
+      * O: 'nothing' = 1 everywhere, data cells get the time-and-space average of each odor bin (strict inequalities, :250-255),
+        the goal state observes 'goal' (:262-275);  uniform start probabilities (:277-279).
+    '''
+    env = agent.environment
+    thr = agent.thresholds
+    action_set = np.asarray(agent.action_set)
+    assert not agent.space_aware, 'This model is not compatible with space_aware agents as the observations would not match the expected observations of this model.'
+    assert thr.ndim == 1, 'This model doesnt allow for layer specific thresholds.'
+    shape = np.array(env.shape)
+    partitions = np.array(partitions)
+    if margin_partitions:
+        cell_shape = (np.array(env.data_shape) / partitions).astype(int)
+        bounds = [np.array([0, *((np.arange(n + 1) * cell_shape[ax]) + env.margins[ax, 0]), shape[ax]]) for ax, n in enumerate(partitions)]
+        cell_counts = int(np.prod(partitions + 2))
+    else:
+        cell_shape = (shape / partitions).astype(int)
+        bounds = [np.arange(n + 1) * cell_shape[ax] for ax, n in enumerate(partitions)]
+        cell_counts = int(np.prod(partitions))
+    # cell ids follow the reference's meshgrid(indexing='xy') order: the FIRST axis varies fastest
+    grid_cells = np.full(env.shape, -1)
+    cell = 0
+    for x0, x1 in zip(bounds[1][:-1], bounds[1][1:]):
+        for y0, y1 in zip(bounds[0][:-1], bounds[0][1:]):
+            grid_cells[y0:y1, x0:x1] = cell
+            cell += 1
+
+    S, A = cell_counts + 1, len(action_set)
+    yy, xx = np.meshgrid(np.arange(env.shape[0]), np.arange(env.shape[1]), indexing='ij')
+    points = np.stack([yy.ravel(), xx.ravel()], axis=1)
+    point_cell = grid_cells[points[:, 0], points[:, 1]]
+    moves = action_set[:, 1:] if env.has_layers else action_set
+    T = np.full((S, A, S), -1.0)
+    for a, mv in enumerate(moves):
+        new_points = env.move(points, mv[None, :])
+        new_cell = grid_cells[new_points[:, 0], new_points[:, 1]]
+        at_source = env.source_reached(new_points)
+        for c in range(cell_counts):
+            inside = point_cell == c
+            count = np.sum(inside)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                T[c, a, :cell_counts] = np.bincount(new_cell[inside & ~at_source & (new_cell >= 0)], minlength=cell_counts) / count
+                T[c, a, -1] = np.sum(inside & at_source) / count
+    T[-1, :, :] = 0.0
+    T[-1, :, -1] = 1.0
+
+    O = len(thr)                                   # bins + goal
+    labels = ['nothing'] + ([f'something_l{i}' for i in range(O - 2)] if O > 3 else ['something']) + ['goal']
+    obs = np.zeros((S, A, O))
+    obs[:-1, :, 0] = 1.0
+    data_bounds = [np.arange(n + 1) * cell_shape[ax] for ax, n in enumerate(partitions)]
+    cell_obs = []
+    for x0, x1 in zip(data_bounds[1][:-1], data_bounds[1][1:]):
+        for y0, y1 in zip(data_bounds[0][:-1], data_bounds[0][1:]):
+            levels = []
+            for lo, hi in zip(thr[:-1], thr[1:]):
+                if env.has_layers:
+                    block = env.data[:, :, y0:y1, x0:x1]
+                    levels.append(np.average((block > lo) & (block < hi), axis=(1, 2, 3)))
+                else:
+                    block = env.data[:, y0:y1, x0:x1]
+                    levels.append(np.average((block > lo) & (block < hi)))
+            cell_obs.append(levels)
+    data_cell_ids = np.arange(cell_counts).reshape(partitions + 2)[1:-1, 1:-1].ravel()
+    for i, cid in enumerate(data_cell_ids):
+        if env.has_layers:
+            layers = action_set[:, 0].astype(int)
+            for o in range(O - 1):
+                obs[cid, :, o] = np.asarray(cell_obs[i][o])[layers]
+        else:
+            obs[cid, :, :O - 1] = cell_obs[i]
+    obs[-1, :, -1] = 1.0
+
+    start = np.ones(S) / S
+    return POMDP(states=[f'cell_{c}' for c in range(cell_counts)] + ['goal'], actions=agent.action_labels, observations=labels,
+                 transition_table=T, observation_table=obs, end_states=[cell_counts], start_probabilities=start)

@@ -483,6 +483,10 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
     OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL, "belief_step: n out of range");
     OLF_REQUIRE((((uintptr_t)b_in | (uintptr_t)b_out) & 15) == 0, "belief_step: belief buffers must be 16-byte aligned");
     if (n == 0) return OLFNAV_OK;
+    if (m->dense) {
+        OLF_CUDA(cudaSetDevice(m->device));
+        return olf_dense_belief_step(m, b_in, b_out, ld, n, act, obs, src_rows, dst_rows, scale_in, scale_out, ok, n_dev, (cudaStream_t)stream);
+    }
     const bool inplace = (b_in == b_out);
     if (inplace && m->g.W4 > BS_THREADS * BS_UNROLL) {
         olfnav_set_error("belief_step: in-place update needs W <= %d", 4 * BS_THREADS * BS_UNROLL);

@@ -7,6 +7,6 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
     -Xcompiler -fPIC -shared \
     "$@" \
-    "$HERE/model.cu" "$HERE/belief.cu" "$HERE/evaluate.cu" "$HERE/solver.cu" "$HERE/infotaxis.cu" "$HERE/umma_gemm.cu" "$HERE/sim.cu" "$HERE/fused_step.cu" \
+    "$HERE/model.cu" "$HERE/belief.cu" "$HERE/evaluate.cu" "$HERE/solver.cu" "$HERE/infotaxis.cu" "$HERE/umma_gemm.cu" "$HERE/sim.cu" "$HERE/fused_step.cu" "$HERE/dense.cu" \
     -o "$OUT"
 echo "built $OUT"

@@ -66,6 +66,11 @@ struct olfnav_model {
     float* pull_lo;
     int pull_rows, pull_rows_p;
     int64_t pull_ld;
+    // dense stochastic-transition models (dense.cu; reference minimal_converter): T[s, a, s'] as [A][S][Sp] planes,
+    // t_pull rows = source state s (contiguous in s'), t_push rows = destination state s' (contiguous in s)
+    int dense;
+    float* t_pull;
+    float* t_push;
 };
 
 struct olfnav_alphas {
@@ -141,3 +146,13 @@ int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float
 int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const float* b_in, float* b_out, int64_t ld, int64_t n,
                           const int32_t* act, const int32_t* obs, const int32_t* src_rows, const float* scale_in, float* scale_out,
                           uint8_t* ok, float* value, int32_t* arg, int32_t* action, const int* n_dev, cudaStream_t st);
+// dense-model kernels (dense.cu)
+int olf_dense_belief_step(const olfnav_model* m, const float* b_in, float* b_out, int64_t ld, int64_t n, const int32_t* act,
+                          const int32_t* obs, const int32_t* src_rows, const int32_t* dst_rows, const float* scale_in,
+                          float* scale_out, uint8_t* ok, const int* n_dev, cudaStream_t st);
+int olf_dense_vi_sweep(const olfnav_model* m, const double* Q_in, double* Q_out, int64_t ld_q, double discount, double* max_change,
+                       cudaStream_t st);
+int olf_dense_backup_gamma(const olfnav_model* m, const float* alpha, int64_t ld_alpha, int G, float discount, float* gamma_ao,
+                           int64_t ld_gamma, cudaStream_t st);
+int olf_dense_infotaxis(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale, int32_t* action, float* dH,
+                        cudaStream_t st);

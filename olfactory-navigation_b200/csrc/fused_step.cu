@@ -616,7 +616,7 @@ int launch_fused(const CUtensorMap& tBh, const CUtensorMap& tBl, const FusedPara
 }  // namespace
 
 extern "C" int olfnav_can_fuse_policy(const olfnav_model* m, const olfnav_alphas* a) {
-    return (m && a && a->Gp <= FUSED_MAX_BN && m->g.Sp >= m->g.Wp + FWIN + 8) ? 1 : 0;
+    return (m && a && !m->dense && a->Gp <= FUSED_MAX_BN && m->g.Sp >= m->g.Wp + FWIN + 8) ? 1 : 0;
 }
 
 // n = upper bound of the rows (grid size), n_dev (optional) = exact device-side count.

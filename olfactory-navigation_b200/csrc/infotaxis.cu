@@ -171,6 +171,7 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
     if (n == 0) return OLFNAV_OK;
     OLF_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->dense) return olf_dense_infotaxis(m, b, ld, n, scale, action, dH, st);
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_INFOTAXIS_V1"); return e && e[0] == '1'; }();
     if (!force_v1 && m->pull_rows <= 128) {
         float* sums = nullptr;

@@ -165,7 +165,7 @@ extern "C" void olfnav_model_destroy(olfnav_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
-    cudaFree(m->pull_hi); cudaFree(m->pull_lo);
+    cudaFree(m->pull_hi); cudaFree(m->pull_lo); cudaFree(m->t_pull); cudaFree(m->t_push);
     delete m;
 }
 

@@ -162,6 +162,7 @@ extern "C" int olfnav_vi_sweep(const olfnav_model* m, const double* Q_in, double
                                double* max_change, void* stream) {
     OLF_REQUIRE(m && Q_in && Q_out && max_change && ld_q >= m->g.Sp, "vi_sweep: bad argument");
     OLF_CUDA(cudaSetDevice(m->device));
+    if (m->dense) return olf_dense_vi_sweep(m, Q_in, Q_out, ld_q, discount, max_change, (cudaStream_t)stream);
     vi_sweep_kernel<<<olf_div_up(m->g.Sp, 256), 256, 0, (cudaStream_t)stream>>>(m->g, m->reward, Q_in, Q_out, ld_q, discount, max_change);
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
@@ -173,6 +174,7 @@ extern "C" int olfnav_backup_gamma(const olfnav_model* m, const float* alpha, in
     OLF_REQUIRE(ld_alpha >= m->g.Sp && ld_gamma >= m->g.Sp && (ld_gamma % 4) == 0, "backup_gamma: bad leading dimension");
     OLF_REQUIRE(G <= 65535, "backup_gamma: G too large");
     OLF_CUDA(cudaSetDevice(m->device));
+    if (m->dense) return olf_dense_backup_gamma(m, alpha, ld_alpha, G, discount, gamma_ao, ld_gamma, (cudaStream_t)stream);
     dim3 grid(olf_div_up(ld_gamma, 256), G, m->g.A);
     backup_gamma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m->g, m->obs, alpha, ld_alpha, G, discount, gamma_ao, ld_gamma);
     OLF_LAUNCH_CHECK();

@@ -4,9 +4,9 @@ POMDP, Belief, BeliefSet, ValueFunction.  Host-visible attributes keep the refer
 (float64 / int64 NumPy, state-major); the arithmetic runs in the CUDA library through the C ABI
 (include/olfnav_b200.h).  Nothing here imports oracle/.
 
-Only grid models with one deterministic successor per (state, action) — what
-`exact_converter` builds (reference agents/model_based_util/environment_converter.py:7-134) —
-are supported; anything else raises NotImplementedError.
+Two model families: grid models with one deterministic successor per (state, action) — what `exact_converter` builds
+(reference agents/model_based_util/environment_converter.py:7-134; stencil kernels) — and dense stochastic-transition
+models over a flat state list — what `minimal_converter` builds (:137-292; dense kernels, csrc/dense.cu).
 '''
 from __future__ import annotations
 
@@ -40,12 +40,15 @@ class POMDP:
                  start_probabilities: np.ndarray = None,
                  grid_shape: tuple = None, moves: np.ndarray = None, boundary: str = None) -> None:
         arr = np.array(states, dtype=object) if not isinstance(states, (int, np.integer)) else None
+        self.dense = transition_table is not None          # dense stochastic transitions (minimal_converter): flat state list
         if arr is not None and arr.ndim == 2:
             gshape = arr.shape
         elif grid_shape is not None:
             gshape = tuple(grid_shape)
+        elif self.dense:
+            gshape = (1, int(states) if arr is None else len(arr))
         else:
-            raise NotImplementedError('only 2-D grid models are supported by the B200 path')
+            raise NotImplementedError('a flat state list needs a transition_table (dense model); grid models need a 2-D state grid')
         if grid_shape is not None:
             gshape = tuple(int(v) for v in grid_shape)
         self.state_count = int(gshape[0] * gshape[1])
@@ -61,8 +64,28 @@ class POMDP:
         self.observations = np.arange(self.observation_count)
         S, A, O = self.state_count, self.action_count, self.observation_count
 
-        if transition_table is not None or reachable_states_table is None:
-            raise NotImplementedError('dense / stochastic transition tables are out of scope (SURVEY §8 f4)')
+        if self.dense:
+            # POMDP(..., transition_table = T[s, a, s']) as called at environment_converter.py:282-290: every state is "reachable",
+            # with probability T (so sampling walks the cumulative sum of the row, like the oracle's)
+            self._transition_table = np.ascontiguousarray(transition_table, dtype=np.float64)
+            assert self._transition_table.shape == (S, A, S), 'transition_table must be (S, A, S)'
+            self.reachable_states = np.broadcast_to(np.arange(S)[None, None, :], (S, A, S))
+            self.reachable_state_count = S
+            self.reachable_probabilities = self._transition_table
+            self.observation_table = np.ascontiguousarray(observation_table, dtype=np.float64)
+            assert self.observation_table.shape == (S, A, O)
+            self.end_states = np.asarray([] if end_states is None else end_states, dtype=np.int64)
+            self.end_mask = np.zeros(S, dtype=bool)
+            self.end_mask[self.end_states] = True
+            self.expected_rewards_table = np.sum(self._transition_table * self.end_mask[None, None, :], axis=2)
+            self.start_probabilities = (np.full(S, 1.0 / S) if start_probabilities is None
+                                        else np.ascontiguousarray(start_probabilities, dtype=np.float64).ravel())
+            self.moves, self.boundary = None, None
+            self.is_on_gpu = True
+            self._handles = {}
+            return
+        if reachable_states_table is None:
+            raise NotImplementedError('a model needs a reachable_states_table (grid) or a transition_table (dense)')
         R = np.asarray(reachable_states_table, dtype=np.int64)
         if R.ndim == 2:
             R = R[:, :, None]
@@ -122,6 +145,12 @@ class POMDP:
             h = ctypes.c_void_p()
             H, W = self.grid_shape
             end = np.ascontiguousarray(self.end_mask.astype(np.uint8))
+            if self.dense:
+                check(lib.olfnav_model_create_dense(ctypes.byref(h), device, self.state_count, self.action_count, self.observation_count,
+                                                    ptr(self._transition_table), ptr(self.observation_table), ptr(end),
+                                                    ptr(self.start_probabilities)))
+                self._handles[device] = _Handle(h, lib.olfnav_model_destroy)
+                return self._handles[device].h
             check(lib.olfnav_model_create(ctypes.byref(h), device, H, W, self.action_count, self.observation_count,
                                           ptr(self.moves), _lib.BOUNDARY[self.boundary], ptr(self.observation_table),
                                           ptr(end), ptr(self.start_probabilities)))
@@ -134,8 +163,20 @@ class POMDP:
         return state
 
     # sampling helpers (host side, inverse CDF on a uniform draw; same convention as the oracle's)
+    @property
+    def transition_table(self) -> np.ndarray:
+        if self.dense:
+            return self._transition_table
+        tt = np.zeros((self.state_count, self.action_count, self.state_count))
+        tt[np.arange(self.state_count)[:, None], np.arange(self.action_count)[None, :], self.reachable_states[:, :, 0]] = 1.0
+        return tt
+
     def transition(self, s: int, a: int, u: float = 0.0) -> int:
-        return int(self.reachable_states[s, a, 0])
+        "s' ~ T(.|s, a) by inverse CDF from the uniform draw u (deterministic on grid models)."
+        if not self.dense:
+            return int(self.reachable_states[s, a, 0])
+        cdf = np.cumsum(self._transition_table[s, a])
+        return min(int(np.searchsorted(cdf, u * cdf[-1], side='right')), self.state_count - 1)
 
     def observe(self, s_p: int, a: int, u: float) -> int:
         cdf = np.cumsum(self.observation_table[s_p, a])

@@ -307,7 +307,7 @@ class FSVI(_PBVI):
         seq = []
         for _ in range(max_generation):
             a = int(np.argmax(Q[:, s]))
-            s_p = model.transition(s, a)
+            s_p = model.transition(s, a, rng.random() if model.dense else 0.0)
             o = model.observe(s_p, a, rng.random())
             seq.append((a, o))
             s = s_p
@@ -339,7 +339,7 @@ class PBVI_SSRA(_PBVI):
             cdf = np.cumsum(dense[k])
             s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
             a = cls.choose_action(model, k, belief_set, alphas, actions, rng, **kw)
-            s_p = model.transition(s, a)
+            s_p = model.transition(s, a, rng.random() if model.dense else 0.0)
             o = model.observe(s_p, a, rng.random())
             nb = _chain_updates(model, belief_set, k, [(a, o)])
             pieces = nb if pieces is None else pieces.union(nb)
@@ -457,7 +457,7 @@ class PBVI_SSEA(_PBVI):
             cdf = np.cumsum(dense[k])
             for a in range(A):
                 s = min(int(np.searchsorted(cdf, rng.random() * cdf[-1], side='right')), model.state_count - 1)
-                s_p = model.transition(s, a)
+                s_p = model.transition(s, a, rng.random() if model.dense else 0.0)
                 obss.append(model.observe(s_p, a, rng.random()))
                 rows.append(k)
                 acts.append(a)
@@ -540,7 +540,7 @@ class Perseus(_PBVI):
                 a = int(vf.evaluate_device(cur)[2][0])
             else:
                 a = min(int(rng.random() * model.action_count), model.action_count - 1)
-            s_p = model.transition(s, a)
+            s_p = model.transition(s, a, rng.random() if model.dense else 0.0)
             o = model.observe(s_p, a, rng.random())
             cur = _chain_updates(model, cur, 0, [(a, o)])
             out = cur if out is None else out.union(cur)
