@@ -378,7 +378,67 @@ fused_step_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
                 mbar_wait_warp(bar_sfull(s), (it / FSA) & 1);
                 TS(3 + gi, 1);
                 float* stg = reinterpret_cast<float*>(gbase + L::A_OFFSET + s * FA_STAGE_BYTES);
-                if (!(p.dbg & 2)) {
+                // Fast path (C2 / C5: cyclic y, clipped x, every row of the tile valid, whole chunk inside the row, likelihood slices
+                // staged): BRANCH-FREE row code, so that the four rows of an iteration form one basic block and their dependency
+                // chains interleave (with uniform branches per row the compiler serialises the rows: ~380 cycles per row visit,
+                // measured).  The boundary columns become chunk-invariant per-lane masks.
+                const bool fast = WRAPY && !WRAPX && smem_tables && (p.dbg & ~1024) == 0 && (tile + 1) * BM <= n && (kc + 1) * FKC <= Sp;
+                if (fast) {
+                    const int ek = e & 3;
+                    const float* tabs = reinterpret_cast<const float*>(gbase + L::TAB_OFFSET + s * (FUSED_SMEM_TABLES * FKC * 4)) + 4 * lane;
+                    float* wrow = stg + tw * FPITCH + FHALO;
+                    float* orow = out_tile + d;
+                    const bool first_col = c4 == 0, last_col = c4 == W4 - 1, lane0 = lane == 0, lane31 = lane == 31;
+                    // dx > 0: the clipped cell W - 1 keeps its own mass (one component of the last float4 of a grid row)
+                    const float kx = (c4 == e4 && ek == 0) ? 1.f : 0.f, ky = (c4 == e4 && ek == 1) ? 1.f : 0.f;
+                    const float kz = (c4 == e4 && ek == 2) ? 1.f : 0.f, kw = (c4 == e4 && ek == 3) ? 1.f : 0.f;
+                    const float k0 = first_col ? 1.f : 0.f;      // dx < 0: cell 0 keeps its own mass
+#pragma unroll 1
+                    for (int i0 = 0; i0 < 16; i0 += 4) {
+                        float4 cur[4], lk[4], rr[4];
+                        float hl[4], hr[4], sc[4];
+                        int mv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float* w = wrow + u * (8 * FPITCH);
+                            cur[u] = *reinterpret_cast<const float4*>(w + 4 * lane);
+                            hl[u] = w[-1]; hr[u] = w[FKC];
+                            mv[u] = rp_move[tw + 8 * (i0 + u)]; sc[u] = rp_sc[tw + 8 * (i0 + u)];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) lk[u] = *reinterpret_cast<const float4*>(tabs + (mv[u] >> 8));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 c = cur[u];
+                            const bool dxp = (mv[u] & 2) != 0, dxn = (mv[u] & 4) != 0;
+                            float left = __shfl_up_sync(0xffffffffu, c.w, 1);
+                            float right = __shfl_down_sync(0xffffffffu, c.x, 1);
+                            left = lane0 ? hl[u] : left;
+                            right = lane31 ? hr[u] : right;
+                            left = first_col ? 0.f : left;
+                            right = last_col ? 0.f : right;
+                            const float fp = dxp ? 1.f : 0.f, fn = dxn ? 1.f : 0.f;
+                            float4 out;
+                            out.x = dxp ? left : (dxn ? c.y : c.x);
+                            out.y = dxp ? c.x : (dxn ? c.z : c.y);
+                            out.z = dxp ? c.y : (dxn ? c.w : c.z);
+                            out.w = dxp ? c.z : (dxn ? right : c.w);
+                            out.x += (fp * kx + fn * k0) * c.x;
+                            out.y += (fp * ky) * c.y;
+                            out.z += (fp * kz) * c.z;
+                            out.w += (fp * kw) * c.w;
+                            const float s1 = sc[u];
+                            rr[u].x = out.x * s1 * lk[u].x; rr[u].y = out.y * s1 * lk[u].y; rr[u].z = out.z * s1 * lk[u].z; rr[u].w = out.w * s1 * lk[u].w;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            *reinterpret_cast<float4*>(wrow + u * (8 * FPITCH) + 4 * lane) = rr[u];
+                            st_stream4(orow + (long long)(8 * u) * p.ld, rr[u]);
+                        }
+                        wrow += 32 * FPITCH;
+                        orow += 32 * p.ld;
+                    }
+                } else if (!(p.dbg & 2)) {
                     // Four rows per iteration: loads first, then four independent dependency chains, then the stores.  The kernel is
                     // instruction-issue bound here (measured), so the body is kept lean: moves are warp-uniform branches, boundary
                     // columns are real (rare) branches, likelihoods come from the staged table slices.
