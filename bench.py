@@ -193,7 +193,7 @@ def measure_backup(onb, model, world, rank, dev, args):
     tf32_peak = peaks.get('bf16_tflops', 1590.0) / 2.0
     issued = 3.0 * flops / (ms * 1e-3) / 1e12 / world
     return {'value': B / (ms * 1e-3), 'unit': 'belief-backups/s', 'belief_points': B, 'alpha_vectors': G, 'ms_per_backup': ms, 'scaling': 'strong',
-            'collective': 'all_gather of the new alpha vectors (B/N x Sp f32 + actions) per backup' if world > 1 else 'none (1 rank)',
+            'collective': 'all_gather of the per-belief selection ((1 + A*O) int32 per belief point: best action + alpha indices) per backup; every rank assembles all new alpha vectors from its own Gamma' if world > 1 else 'none (1 rank)',
             'roofline': {'kernel': 'umma_ts_kernel', 'bound': 'tensor', 'achieved': issued, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': issued / tf32_peak,
                          'note': 'issued TF32 flop (3 passes of the split-precision scheme) per GPU over the WHOLE backup time (Gamma build, GEMM, assembly, all-gather); '
                                  'peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)'}}

@@ -140,6 +140,41 @@ def backup_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tensor, gam
     return new_alpha, best_a, best_v, best_g
 
 
+def backup_select_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tensor, gamma: float, path: int = 0):
+    '''
+    The first two thirds of backup_device: Gamma build + per-belief selection.  Returns (gam, best_g (B, A, O), best_a (B,), best_v (B,));
+    backup_assemble_device turns (gam, best_g, best_a) — of ANY belief points, e.g. gathered from other ranks — into alpha vectors.
+    '''
+    device = belief_set.device
+    dev = torch.device('cuda', device)
+    h = model.handle(device)
+    A, O, Sp = model.action_count, model.observation_count, model.padded_states
+    G, B = alphas.shape[0], len(belief_set)
+    gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=dev)
+    best_g = torch.empty((max(B, 1), A, O), dtype=torch.int32, device=dev)
+    best_a = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+    best_v = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(device):
+        check(lib.olfnav_backup_gamma(h, ptr(alphas), alphas.stride(0), G, gamma, ptr(gam), Sp, stream()))
+        if B:
+            check(lib.olfnav_backup_select(h, ptr(belief_set._b), belief_set.ld, B, ptr(belief_set._scale), ptr(gam), Sp, G,
+                                           ptr(best_g), ptr(best_a), ptr(best_v), path, stream()))
+    return gam, best_g[:B], best_a[:B], best_v[:B]
+
+
+def backup_assemble_device(model: POMDP, gam: torch.Tensor, G: int, best_g: torch.Tensor, best_a: torch.Tensor, device: int = None):
+    'alpha_b = r_{a*} + sum_o Gamma[a*][o][g*(b, a*, o)] for every row of (best_g, best_a).'
+    device = current_device() if device is None else device
+    Sp = model.padded_states
+    B = int(best_a.shape[0])
+    new_alpha = torch.empty((B, Sp), dtype=torch.float32, device=gam.device)
+    if B:
+        with torch.cuda.device(device):
+            check(lib.olfnav_backup_assemble(model.handle(device), ptr(gam), Sp, G, ptr(best_g.contiguous()), ptr(best_a.contiguous()), B,
+                                             ptr(new_alpha), Sp, stream()))
+    return new_alpha
+
+
 def _unique_rows(alpha: torch.Tensor, actions: torch.Tensor):
     'Drop exact duplicate (vector, action) rows, keep the first occurrence and the original order.'
     if alpha.shape[0] <= 1:

@@ -30,10 +30,11 @@ for _ in range(4):
     bs = bs.update(rng.integers(0, m.action_count, B), np.zeros(B, dtype=int))
 alphas = agent.value_function.device_alphas()
 full_alpha, full_a, _, _ = onb.solvers.backup_device(m, bs, alphas, 0.99)
-sh_alpha, sh_a = parallel.backup_sharded(m, bs, alphas, 0.99)
-assert sh_alpha.shape == full_alpha.shape, (sh_alpha.shape, full_alpha.shape)
-assert torch.equal(sh_a, full_a), 'sharded backup: actions differ'
-assert torch.equal(sh_alpha, full_alpha), 'sharded backup: alpha vectors differ'
+for exchange in ('indices', 'alphas'):
+    sh_alpha, sh_a = parallel.backup_sharded(m, bs, alphas, 0.99, exchange=exchange)
+    assert sh_alpha.shape == full_alpha.shape, (sh_alpha.shape, full_alpha.shape)
+    assert torch.equal(sh_a, full_a), f'sharded backup ({exchange}): actions differ'
+    assert torch.equal(sh_alpha, full_alpha), f'sharded backup ({exchange}): alpha vectors differ'
 
 # ---- simulation ----
 n = 203
