@@ -148,7 +148,9 @@ extern "C" void olfnav_alphas_destroy(olfnav_alphas* a) {
 
 int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n, const float* scale,
                       float* val, int* idx, float* value, int32_t* arg, int32_t* action, int path, cudaStream_t st) {
-    if (path == 0) path = (a->G <= 8) ? 1 : 2;
+    // auto: FP32 SIMT for a handful of alpha vectors on small batches (lower latency), tcgen05 otherwise — at 100 000 rows the
+    // tensor path streams at 89 % of HBM even for G = 4 (SIMT: 79 %, scripts/bench_rows.py)
+    if (path == 0) path = (a->G <= 8 && n < 8192) ? 1 : 2;
     int rc;
     if (path == 1) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, a->full, a->ld, 1, a->G, val, idx, st);
     else           rc = olf_umma_segmax(b, ld, n, m->g.Sp, a->hi, a->lo, a->ld, a->Gp, 1, a->G, a->Gp, val, idx, m->sm_count, st);
