@@ -8,13 +8,15 @@
 // sum is a one-cell stencil shift with edge accumulation ("push"): under clip the downstream edge
 // cells receive two sources and the upstream edge cells none; under wrap the shift is cyclic.
 //
-// One CTA per agent.  The belief row is streamed once (read 4 B + write 4 B per state, 128-bit
-// accesses) in chunks of whole grid rows.  The x-shift is done in registers with warp shuffles, the
-// y-shift is a float4-aligned pointer offset thanks to the padded row layout, the likelihood is a
-// read of the (L2-resident) observation table, and the per-agent normaliser is a shuffle+smem block
-// reduction.  Normalisation is deferred: the row is stored unnormalised and 1/Z goes to scale[].
-// Chunks are visited in the direction that makes the update safe IN PLACE (needed for 10^6 agents
-// on 83x371: 123 GB of beliefs on a 180 GB part).
+// One CTA per agent.  The belief row is streamed once (read 4 B + write 4 B per state, 128-bit accesses) in chunks of whole
+// grid rows.  Production kernel: belief_step_tma_kernel — the source rows of the next three chunks are always in flight as 1-D
+// bulk copies (cp.async.bulk + mbarrier) into a shared-memory ring, the y-shift is a row-aligned offset of the copy (padded row
+// layout), the x-shift a one-element offset of the shared-memory read, the likelihood a read of the (L2-resident) observation
+// table, the per-agent normaliser a shuffle + shared-memory block reduction.  Normalisation is deferred: the row is stored
+// unnormalised and 1/Z goes to scale[].  CTAs start their traversal at different chunks and alternate direction (see the
+// kernel); in place (b_out == b_in, needed for 10^6 agents on 83x371: 123 GB of beliefs on a 180 GB part) the chunk order is the
+// one that reads every source before it is overwritten.  belief_step_kernel (register streaming, x-shift by warp shuffles) is
+// the fallback for grid rows that do not fit a ring stage, and the dense-model kernel lives in dense.cu.
 #include "common.cuh"
 #include "stencil.cuh"
 
