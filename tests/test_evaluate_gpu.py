@@ -142,3 +142,33 @@ def test_vi_918_sweeps(cfg):
     assert len(hist.value_function_changes) == 918
     np.testing.assert_allclose(hist.value_function_changes, g['changes'], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(vf.alpha_vector_array, g['Q'], rtol=1e-6)
+
+
+def test_backup_full_size_properties():
+    '''
+    BASELINE C3 shape (83x371 states, wrap_vertical), 2 000 belief points against 64 alpha vectors — size-independent properties of the
+    backup: (1) the value reported for a point is the value of ITS new vector at that point (selection and assembly are consistent);
+    (2) with non-negative alpha vectors the new vector is worth at least the best immediate reward at its point; (3) padding
+    columns of the new vectors are zero.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C2')
+    m = agent.model
+    rng = np.random.default_rng(4)
+    B, G = 2000, 64
+    bs = onb.BeliefSet(m, B)
+    for _ in range(5):
+        bs = bs.update(rng.integers(0, 4, B), (rng.random(B) < 0.15).astype(int), raise_on_impossible_belief=False)
+    n = len(bs)
+    alphas = torch.as_tensor(np.abs(rng.standard_normal((G, m.padded_states))).astype(np.float32), device=bs._b.device)
+    H, W = m.grid_shape
+    alphas.view(G, H, -1)[:, :, W:] = 0
+    new_alpha, best_a, new_v, best_g = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    dense = bs.belief_tensor(torch.float64)                                       # normalised rows (n, S), reference state order
+    na = new_alpha.view(n, H, -1)[:, :, :W].reshape(n, -1).double()
+    at_point = (dense * na).sum(1)
+    np.testing.assert_allclose(new_v.double().cpu().numpy(), at_point.cpu().numpy(), rtol=2e-5)
+    assert float(new_alpha.view(n, H, -1)[:, :, W:].abs().max()) == 0.0
+    r = torch.as_tensor(m.expected_rewards_table.T.copy(), device=dense.device)    # (A, S)
+    immediate = (dense @ r.T).max(1).values
+    assert bool((at_point >= immediate - 1e-6).all())                              # alphas >= 0: the backup can only add to the immediate reward
