@@ -70,7 +70,7 @@ if 'evaluate' in rows:
 if 'backup' in rows:
     B = 10_000
     bs = evolved_beliefs(B, steps=6)
-    for G in (64, 256, 1000):
+    for G in (64, 256, 512, 1000, 2048):
         alphas = torch.as_tensor(np.abs(rng.standard_normal((G, Sp))).astype(np.float32), device=dev)
         t = timeit(lambda: onb.solvers.backup_device(m, bs, alphas, 0.99, 2), iters=3, warm=1)
         flops = 2.0 * B * S * G * m.action_count * m.observation_count
