@@ -42,6 +42,7 @@ struct StepArgs {
     int n;
     int stagger;
     int rot;               // > 0: CTA i starts its traversal at chunk (i * rot) % nchunks (where the order is free)
+    int rot_inplace;       // ... and in place with dy != 0 (cyclic order + one stashed source row): 1 always, 0 never, -1 on wide grids
     int inplace;
     const int* n_dev;      // optional device-side row count: CTAs with blockIdx.x >= *n_dev exit (grid sized by an upper bound)
 };
@@ -238,8 +239,9 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
     constexpr int BS2_STAGE_FLOATS = BS2_THREADS * BS2_UNROLL * 4;     // 16 KB (256 threads) or 32 KB (512 threads)
     extern __shared__ __align__(128) float smem[];
     float* stage_base = smem;                                        // BS2_STAGES x BS2_STAGE_FLOATS
-    float* halo = smem + BS2_STAGES * BS2_STAGE_FLOATS;              // Wp floats
-    float* red = halo + g.Wp;                                        // 40 floats
+    float* halo = smem + BS2_STAGES * BS2_STAGE_FLOATS;              // Wp floats: the wrapped source row
+    float* stash = halo + g.Wp;                                      // Wp floats: the one source row a rotated in-place traversal overwrites early
+    float* red = stash + g.Wp;                                       // 40 floats
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 40);          // BS2_STAGES mbarriers (8-byte aligned: Wp % 4 == 0)
 
     const int tid = threadIdx.x;
@@ -264,16 +266,23 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
     // lockstep, and the read and write streams then collide in DRAM: 64-78 % of the HBM bandwidth on uniform actions (measured,
     // C2 and C5).  Where the order is free (out of place, or dy == 0) CTA i therefore starts at chunk (i * rot) % nchunks and
     // neighbouring CTAs alternate direction: 97-100 % on every action pattern (profiles/r1j_rot_sweep.jsonl).  In place with
-    // dy != 0 the order is dictated by the move (sources are read before they are overwritten: descending for dy > 0,
-    // ascending for dy < 0); there the chunk SIZE varies with the CTA index instead, which dephases the CTAs over time
-    // (C2 98.6 %, C5 87 %).
+    // dy != 0 the direction is dictated by the move (sources are read before they are overwritten: descending for dy > 0,
+    // ascending for dy < 0) but the start is rotated too (see `rot` below); with rot = 0 the chunk SIZE varies with the CTA
+    // index instead, which dephases the CTAs over time (C2 98.6 %, C5 87 %).
     const int rpc_max = max(1, (BS2_THREADS * BS2_UNROLL) / W4);
     const bool free_dir = !p.inplace || dy == 0;
-    const int rpc = max(1, rpc_max - ((!free_dir && p.stagger > 1) ? (int)(blockIdx.x % (unsigned)p.stagger) : 0));
+    // in place with dy != 0: rotate where the per-CTA chunk-size stagger would leave small chunks (wide grids: C5 89 % -> 98 %);
+    // on C2 (11 rows per chunk) the stagger is as good (98 % vs 96 %), so it stays
+    const bool may_rotate = p.rot > 0 && (free_dir || p.rot_inplace == 1 || (p.rot_inplace < 0 && rpc_max < 8));
+    const int rpc = max(1, rpc_max - ((!free_dir && !may_rotate && p.stagger > 1) ? (int)(blockIdx.x % (unsigned)p.stagger) : 0));
     const int nrows = hi_row - lo_row;
     const int nchunks = (nrows + rpc - 1) / rpc;
     const bool desc = free_dir ? ((blockIdx.x & 1u) != 0u) : (dy > 0);
-    const int rot = (free_dir && p.rot > 0 && nchunks > 1) ? (int)(((unsigned)blockIdx.x * (unsigned)p.rot) % (unsigned)nchunks) : 0;
+    // The start is rotated in place with dy != 0 as well: the chunks still follow the dictated direction cyclically, and the only source
+    // row that is overwritten before its reader runs — the first row written by the first chunk, needed by the last chunk of the
+    // cycle — is stashed in shared memory by the prologue.
+    const int rot = (may_rotate && nchunks > 1) ? (int)(((unsigned)blockIdx.x * (unsigned)p.rot) % (unsigned)nchunks) : 0;
+    const bool use_stash = !free_dir && rot > 0;
     auto chunk_rows = [&](int k, int& y0, int& y1) {
         k += rot;
         if (k >= nchunks) k -= nchunks;
@@ -307,6 +316,14 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
     float zacc = 0.f;
 
     // ---- prologue (the bulk loads above are already in flight) ------------------------------------------
+    int stash_src = -1;
+    if (use_stash) {
+        int y0r, y1r;
+        chunk_rows(0, y0r, y1r);                        // the first chunk of the rotated cycle
+        stash_src = desc ? y1r - 1 : y0r;               // its first-written row is the source of the row just beyond it
+        for (int c = tid; c < W4; c += BS2_THREADS)
+            reinterpret_cast<float4*>(stash)[c] = ld_stream4(bin + 4 * (stash_src * W4 + c));
+    }
     if (dy != 0) {
         if (g.wrap_y) {
             const int hrow = dy > 0 ? H - 1 : 0;
@@ -359,7 +376,8 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
         }
         const int base4 = y0 * W4;
         const int n4 = (y1 - y0) * W4;
-        const bool special = (y0 - dy < 0) || (y1 - 1 - dy >= H);      // chunk holds a destination row without in-range source
+        const bool stash_chunk = use_stash && k == nchunks - 1;        // the last chunk of a rotated in-place cycle reads the stashed row
+        const bool special = (y0 - dy < 0) || (y1 - 1 - dy >= H) || stash_chunk;   // chunk holds a destination row without a source in its stage
 #pragma unroll
         for (int j = 0; j < BS2_UNROLL; ++j) {
             const int f = tid + j * BS2_THREADS;
@@ -371,7 +389,8 @@ belief_step_tma_kernel(const StepArgs p, const __grid_constant__ Geom g) {
                     const int r = (W4 == 1) ? f : (int)__umulhi((unsigned)f, g.div_w4);
                     const int c4 = f - r * W4;
                     const int ys = y0 + r - dy;
-                    if (ys >= 0 && ys < H) v = xshift_row(stg + (size_t)r * Wp, c4, dx, W, W4, wrap_x);
+                    if (stash_chunk && ys == stash_src) v = xshift_row(stash, c4, dx, W, W4, wrap_x);
+                    else if (ys >= 0 && ys < H) v = xshift_row(stg + (size_t)r * Wp, c4, dx, W, W4, wrap_x);
                     else if (g.wrap_y)     v = xshift_row(halo, c4, dx, W, W4, wrap_x);
                     else                   v = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -503,6 +522,7 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
     p.stagger = stagger;
     static const int rot = [] { const char* e = getenv("OLFNAV_BELIEF_ROT"); return e ? atoi(e) : 7; }();
     p.rot = rot;
+    { const char* e = getenv("OLFNAV_BELIEF_ROT_INPLACE"); p.rot_inplace = e ? (e[0] == '1' ? 1 : 0) : -1; }
     p.inplace = inplace ? 1 : 0;
     p.n_dev = n_dev;
     // v2 (TMA ring) whenever a grid row fits one stage; OLFNAV_BELIEF_V1=1 forces the register-streaming v1 kernel.
@@ -512,7 +532,7 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
     const char* ft = getenv("OLFNAV_BELIEF_THREADS");
     const int force_threads = ft ? atoi(ft) : 0;
     auto ring_smem = [&](int threads) {
-        return (size_t)(BS2_STAGES * threads * BS2_UNROLL * 4 + m->g.Wp + 40) * sizeof(float) + BS2_STAGES * sizeof(uint64_t);
+        return (size_t)(BS2_STAGES * threads * BS2_UNROLL * 4 + 2 * m->g.Wp + 40) * sizeof(float) + BS2_STAGES * sizeof(uint64_t);
     };
     const bool fits256 = m->g.W4 <= 256 * BS2_UNROLL && ring_smem(256) <= 56 * 1024;       // 4 CTAs per SM
     const bool fits512 = m->g.W4 <= 512 * BS2_UNROLL && ring_smem(512) <= 112 * 1024;      // 2 CTAs per SM

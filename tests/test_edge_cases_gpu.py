@@ -157,3 +157,44 @@ def test_everybody_finishes_at_once_and_single_agent_run():
     assert bool(np.all(hist.reached_source)) and np.all(np.array(hist.done_at_step) == np.array(hist.done_at_step)[0])
     one = onb.run_test(agent, n=1, start_points=start[:1], time_shift=np.zeros(1, dtype=int), horizon=20, print_progress=False, print_stats=False, batches=1)
     assert bool(one.reached_source[0]) and one.done_at_step[0] == hist.done_at_step[0]
+
+
+@pytest.mark.parametrize('boundary', ['stop', 'wrap_vertical', 'wrap'])
+@pytest.mark.parametrize('rot_inplace', ['0', '1'])
+def test_in_place_rotated_traversal_tall_grid(boundary, rot_inplace, monkeypatch):
+    '''
+    A grid tall enough for several ring chunks per row (200 x 52): in place, CTAs start at different chunks and the one source row that
+    is overwritten early comes from the stash — rows must equal the out-of-place update bit for bit, and the oracle within 1e-5.
+    '''
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    monkeypatch.setenv('OLFNAV_BELIEF_ROT_INPLACE', rot_inplace)      # read per call
+    data = onb.synthetic.plume_frames(8, 180, 32, source_y=90, seed=5)
+    env = onb.Environment(data_file=data, data_source_position=[90, 0], source_radius=2.0, margins=[10, 10], boundary_condition=boundary,
+                          start_zone='data_zone')
+    agent = onb.agents.QMDP_Agent(env, thresholds=0.5)
+    m, om = agent.model, oracle_model(agent.model)
+    assert m.grid_shape == (200, 52)
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(9)
+    n = 600                                                          # more CTAs than chunk offsets: every rotation occurs
+    d = -np.log(1.0 - rng.random((n, m.state_count)))
+    B = (d / d.sum(1, keepdims=True)).astype(np.float32).astype(np.float64)
+    for acts in (np.zeros(n, dtype=int), np.full(n, 2), rng.integers(0, 4, n)):      # all north, all south, mixed
+        obs = np.zeros(n, dtype=int)
+        bs = onb.BeliefSet(m, B)
+        a = torch.as_tensor(acts, dtype=torch.int32, device=dev)
+        o = torch.as_tensor(obs, dtype=torch.int32, device=dev)
+        ok = torch.empty(n, dtype=torch.uint8, device=dev)
+        out_b, out_s = torch.empty_like(bs._b), torch.empty_like(bs._scale)
+        check(lib.olfnav_belief_step(m.handle(0), ptr(bs._b), ptr(out_b), bs.ld, n, ptr(a), ptr(o), None, None, ptr(bs._scale), ptr(out_s), ptr(ok), stream()))
+        ip_b, ip_s = bs._b.clone(), bs._scale.clone()
+        check(lib.olfnav_belief_step(m.handle(0), ptr(ip_b), ptr(ip_b), bs.ld, n, ptr(a), ptr(o), None, None, ptr(ip_s), ptr(ip_s), ptr(ok), stream()))
+        assert torch.equal(ip_b, out_b)
+        assert float(((ip_s - out_s).abs() / out_s).max()) < 1e-6
+        ref = tk.BeliefSet(om, B[:40]).update(acts[:40], obs[:40], raise_on_impossible_belief=False)
+        got = onb.BeliefSet(m, _buffers=(ip_b, ip_s, n), device=0).belief_array[:40]
+        np.testing.assert_allclose(got, ref.belief_array, rtol=1e-5, atol=1e-30)
