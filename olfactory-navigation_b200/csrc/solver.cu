@@ -131,11 +131,15 @@ __global__ void backup_assemble_kernel(const Geom g, const float* __restrict__ r
     *reinterpret_cast<float4*>(out + b * ld_out + 4 * (size_t)c) = acc;
 }
 
+// blockIdx.z = segment: source rows seg * rows .. + rows, destination rows seg * gridDim.y .. (segments padded to gridDim.y rows)
 __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
                                     float* __restrict__ hi, float* __restrict__ lo, long long ld) {
     const long long r = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ld) return;
+    src += (long long)blockIdx.z * rows * ld_src;
+    hi += (long long)blockIdx.z * gridDim.y * ld;
+    lo += (long long)blockIdx.z * gridDim.y * ld;
     const float v = (r < rows && c < K) ? src[r * ld_src + c] : 0.f;
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     hi[r * ld + c] = h;
@@ -208,10 +212,9 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
         float *hi = nullptr, *lo = nullptr;
         OLF_CUDA(cudaMallocAsync((void**)&hi, (size_t)nseg * Gs * ldp * sizeof(float), st));
         OLF_CUDA(cudaMallocAsync((void**)&lo, (size_t)nseg * Gs * ldp * sizeof(float), st));
-        for (int s = 0; s < nseg && rc == OLFNAV_OK; ++s) {
-            dim3 grid(olf_div_up(ldp, 256), Gs);
-            split_planes_kernel<<<grid, 256, 0, st>>>(gamma_ao + (long long)s * G * ld_gamma, ld_gamma, G, m->g.Sp,
-                                                      hi + (long long)s * Gs * ldp, lo + (long long)s * Gs * ldp, ldp);
+        {
+            dim3 grid(olf_div_up(ldp, 256), Gs, nseg);           // one launch for all (a, o) segments
+            split_planes_kernel<<<grid, 256, 0, st>>>(gamma_ao, ld_gamma, G, m->g.Sp, hi, lo, ldp);
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: split launch failed"); rc = OLFNAV_ERR_CUDA; }
         }

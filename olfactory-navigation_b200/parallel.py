@@ -58,18 +58,21 @@ def run_test_sharded(agent, n: int, start_points: np.ndarray, time_shift: np.nda
     return out
 
 
-def all_gather_rows(rows: torch.Tensor, extra: torch.Tensor = None):
+def all_gather_rows(rows: torch.Tensor, extra: torch.Tensor = None, counts: list = None):
     '''
     Concatenate a (k_r, D) tensor (k_r may differ per rank) over all ranks, plus an optional (k_r,) companion.
-    One all_gather of the row counts and one padded all_gather of the payload.
+    One padded all_gather of the payload; the row counts are gathered first unless the caller knows them (`counts`, e.g. from
+    shard_bounds: saves a collective and its host synchronisation per backup).
     '''
     rank, ws = world()
     if ws == 1:
         return rows, extra
-    k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    counts = [torch.zeros_like(k) for _ in range(ws)]
-    dist.all_gather(counts, k)
-    counts = [int(c) for c in counts]
+    if counts is None:
+        k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+        counts = [torch.zeros_like(k) for _ in range(ws)]
+        dist.all_gather(counts, k)
+        counts = [int(c) for c in counts]
+    assert len(counts) == ws and counts[rank] == rows.shape[0]
     kmax = max(max(counts), 1)
     pad = torch.zeros((kmax, rows.shape[1]), dtype=rows.dtype, device=rows.device)
     pad[:rows.shape[0]] = rows
@@ -117,7 +120,7 @@ def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: 
     G = alphas.shape[0]
     gam, best_g, best_a, _ = backup_select_device(model, part, alphas, gamma, path)
     packed = torch.cat([best_a[:, None], best_g.reshape(hi - lo, -1)], dim=1).contiguous()       # (B_r, 1 + A*O) int32
-    packed_all, _ = all_gather_rows(packed)
+    packed_all, _ = all_gather_rows(packed, counts=[b - a for a, b in (shard_bounds(len(belief_set), r, ws) for r in range(ws))])
     best_a_all = packed_all[:, 0].contiguous()
     best_g_all = packed_all[:, 1:].contiguous()
     return backup_assemble_device(model, gam, G, best_g_all, best_a_all, belief_set.device), best_a_all

@@ -44,6 +44,9 @@ def _worker(rank: int, ws: int, port: int, q):
         want = torch.cat([torch.full((r + 2, 5), float(r)) + torch.arange(r + 2)[:, None] * 0.1 for r in range(ws)])
         want_a = torch.cat([torch.arange(r + 2, dtype=torch.int32) + 10 * r for r in range(ws)])
         assert torch.equal(got, want) and torch.equal(got_a, want_a)
+        # caller-known counts (shard_bounds): same result without the count collective
+        got2, _ = parallel.all_gather_rows(rows, counts=[r + 2 for r in range(ws)])
+        assert torch.equal(got2, want)
         # empty contribution from one rank
         e, ea = parallel.all_gather_alphas(rows[:0] if rank == 0 else rows, acts[:0] if rank == 0 else acts)
         assert e.shape[0] == sum((r + 2) for r in range(1, ws))
