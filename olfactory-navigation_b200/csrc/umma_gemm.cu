@@ -46,10 +46,31 @@ struct GemmParams {
                                  // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
     float* out_store;            // != NULL: store mode, out_store[row * out_ld + col] = product (col < rows_b); no max / argmax
     long long out_ld;
+    // Tail split (single n tile only): the tiles of the last, partial wave are cut along K into tail_split parts each, so that the
+    // wave is spread over all SMs instead of costing a whole wave on a few (measured: evaluate of 100 000 rows = 5.28 waves ran
+    // as long as 6 full waves).  Units [0, full_units) are whole tiles; unit full_units + t * tail_split + q is part q of tail tile t.
+    // The parts' partial sums go to tail_ws[t][q][row][col] and are added in a fixed order by tail_finish_kernel (deterministic).
+    int full_units, tail_split;
+    float* tail_ws;
 };
+
+// unit id -> k-block range [kb0, kb1) and tail part (-1: whole tile); the tile itself comes from unit_to_tile
+__device__ __forceinline__ int unit_tile_index(const GemmParams& p, int u) {
+    return (p.tail_split > 1 && u >= p.full_units) ? p.full_units + (u - p.full_units) / p.tail_split : u;
+}
+__device__ __forceinline__ void unit_k_range(const GemmParams& p, int u, int& kb0, int& kb1, int& part) {
+    kb0 = 0; kb1 = p.num_k_blocks; part = -1;
+    if (p.tail_split > 1 && u >= p.full_units) {
+        part = (u - p.full_units) % p.tail_split;
+        const int per = (p.num_k_blocks + p.tail_split - 1) / p.tail_split;
+        kb0 = min(part * per, p.num_k_blocks);
+        kb1 = min(kb0 + per, p.num_k_blocks);
+    }
+}
 
 // unit id -> (m tile, n tile)
 __device__ __forceinline__ void unit_to_tile(const GemmParams& p, int u, int& mt, int& nt) {
+    u = unit_tile_index(p, u);
     const int per_group = p.num_m_tiles * p.group_w;
     int g = u / per_group;
     const int n_groups = (p.num_n_tiles + p.group_w - 1) / p.group_w;
@@ -139,9 +160,10 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one_sync()) {
             uint32_t it = 0;
             for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-                int mt, nt;
+                int mt, nt, kbeg, kend, part;
                 unit_to_tile(p, u, mt, nt);
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                unit_k_range(p, u, kbeg, kend, part);
+                for (int kb = kbeg; kb < kend; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(bar_empty(s), ph ^ 1);
@@ -157,13 +179,15 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t idesc = make_idesc_tf32<BN>();
         uint32_t it = 0, ccount = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+            int kbeg, kend, part;
+            unit_k_range(p, u, kbeg, kend, part);
+            for (int kb0 = kbeg; kb0 < kend; kb0 += KCHUNK, ++ccount) {
                 const int acc = ccount & 1;
                 const uint32_t aph = (ccount >> 1) & 1;
                 mbar_wait(bar_tempty(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                const int kb1 = min(KB, kb0 + KCHUNK);
+                const int kb1 = min(kend, kb0 + KCHUNK);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -198,7 +222,9 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t it = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
+            int kbeg, kend, part;
+            unit_k_range(p, u, kbeg, kend, part);
+            for (int kb = kbeg; kb < kend; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 const int ta = it % TA;
@@ -249,7 +275,9 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float sum[BN];
 #pragma unroll
             for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-            for (int kb0 = 0; kb0 < KB; kb0 += KCHUNK, ++ccount) {
+            int kbeg, kend, part;
+            unit_k_range(p, u, kbeg, kend, part);
+            for (int kb0 = kbeg; kb0 < kend; kb0 += KCHUNK, ++ccount) {
                 const int acc = ccount & 1;
                 const uint32_t aph = (ccount >> 1) & 1;
                 mbar_wait(bar_tfull(acc), aph);
@@ -273,6 +301,12 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty(acc));
+            }
+            if (part >= 0) {          // tail part: partial sums of this K range, combined by tail_finish_kernel
+                float* wsrow = p.tail_ws + ((((long long)(unit_tile_index(p, u) - p.full_units) * p.tail_split + part) * BM) + q * 32 + lane) * BN;
+#pragma unroll
+                for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4*>(wsrow + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+                continue;
             }
             if (p.out_store) {
                 if (row_ok) {
@@ -327,6 +361,25 @@ __global__ void segmax_decode_kernel(long long n, const unsigned long long* __re
     u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
     out_val[i] = __uint_as_float(u);
     out_arg[i] = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+}
+
+// Tail tiles: add the K parts in a fixed order, then the same epilogue as the kernel (single n tile: one segment or plain store).
+__global__ void tail_finish_kernel(const GemmParams p, int BN, int tail_tiles) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // row inside the tail
+    if (i >= (long long)tail_tiles * BM) return;
+    const int t = (int)(i / BM), r = (int)(i - (long long)t * BM);
+    const long long row = (long long)(p.full_units + t) * BM + r;
+    if (row >= p.n_rows) return;
+    const float* w = p.tail_ws + ((long long)t * p.tail_split * BM + r) * BN;
+    float best = -INFINITY;
+    int best_idx = 0;
+    for (int j = 0; j < BN; ++j) {
+        float x = 0.f;
+        for (int q = 0; q < p.tail_split; ++q) x += w[(long long)q * BM * BN + j];
+        if (p.out_store) { if (j < p.rows_b) p.out_store[row * p.out_ld + j] = x; }
+        else if (j < p.seg_len && x > best) { best = x; best_idx = j; }
+    }
+    if (!p.out_store) { p.out_val[row] = best; p.out_arg[row] = best_idx; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -410,7 +463,22 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
 
-    const int grid = p.num_units < sm_count ? p.num_units : sm_count;
+    int grid = p.num_units < sm_count ? p.num_units : sm_count;
+    // tail split: single n tile (evaluate, infotaxis), more than one wave, last wave less than ~70 % full
+    p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
+    int tail_tiles = 0;
+    static const bool tail_off = [] { const char* e = getenv("OLFNAV_GEMM_TAIL"); return e && e[0] == '0'; }();
+    if (!tail_off && p.num_n_tiles == 1 && p.n_seg == 1 && p.num_units > sm_count && p.num_k_blocks >= 64) {
+        const int tail = p.num_units % sm_count;
+        const int split = tail ? (sm_count / tail < 4 ? sm_count / tail : 4) : 1;
+        if (tail && split > 1) {
+            tail_tiles = tail;
+            p.full_units = p.num_units - tail;
+            p.tail_split = split;
+            p.num_units = p.full_units + tail * split;
+            OLF_CUDA(cudaMallocAsync((void**)&p.tail_ws, (size_t)tail * split * BM * BN * sizeof(float), st));
+        }
+    }
     // A in tensor memory: shared-memory stage = 16 KB raw A + 2 B planes of BN x 128 B (as many as fit ~216 KB);
     // TMEM holds 64 columns (hi, lo) per A slot next to the two accumulator buffers (512 columns in all)
     switch (BN) {
@@ -422,6 +490,14 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
         case 96:  rc = launch_ts<96, 5, 4>(tA, tBh, tBl, p, grid, st); break;
         case 112: rc = launch_ts<112, 4, 4>(tA, tBh, tBl, p, grid, st); break;
         default:  rc = launch_ts<128, 4, 4>(tA, tBh, tBl, p, grid, st); break;
+    }
+    if (p.tail_ws) {
+        if (rc == OLFNAV_OK) {
+            tail_finish_kernel<<<olf_div_up((int64_t)tail_tiles * BM, 128), 128, 0, st>>>(p, BN, tail_tiles);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma: tail finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        cudaFreeAsync(p.tail_ws, st);
     }
     if (p.ws) {
         if (rc == OLFNAV_OK) {

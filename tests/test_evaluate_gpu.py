@@ -172,3 +172,41 @@ def test_backup_full_size_properties():
     r = torch.as_tensor(m.expected_rewards_table.T.copy(), device=dense.device)    # (A, S)
     immediate = (dense @ r.T).max(1).values
     assert bool((at_point >= immediate - 1e-6).all())                              # alphas >= 0: the backup can only add to the immediate reward
+
+
+@pytest.mark.parametrize('G', [5, 16, 75])
+def test_tail_split_of_the_last_wave(G):
+    '''
+    More than one wave of 128-row tiles (20 000 rows = 157 tiles on 148 SMs): the 9 tiles of the last wave are cut along K into parts
+    that run on different SMs and are added by a finishing kernel.  Values and argmax must agree with the FP32 SIMT path and with
+    the same rows evaluated in a small batch (no split); the infotaxis sums (store mode) go through the same code.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(G)
+    n = 20000
+    bs = onb.BeliefSet(m, n)
+    for _ in range(3):
+        bs = bs.update(rng.integers(0, 4, n), np.zeros(n, dtype=int), raise_on_impossible_belief=False)
+    n = len(bs)
+    alphas = np.abs(rng.standard_normal((G, m.state_count))).astype(np.float32).astype(np.float64)
+    vf = onb.ValueFunction(m, alphas, np.arange(G) % 4)
+    v2, a2, _ = vf.evaluate_device(bs, 2)
+    v1, a1, _ = vf.evaluate_device(bs, 1)
+    np.testing.assert_allclose(v2.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5)
+    assert float((a2 == a1).float().mean()) > 0.999
+    tail = onb.BeliefSet(m, _buffers=(bs._b[n - 1200:n].contiguous(), bs._scale[n - 1200:n].contiguous(), 1200), device=0)
+    vt, at, _ = vf.evaluate_device(tail, 2)
+    np.testing.assert_allclose(v2[n - 1200:].cpu().numpy(), vt.cpu().numpy(), rtol=2e-6)
+    assert float((a2[n - 1200:] == at).float().mean()) > 0.999
+    if G == 5:
+        c = onb.synthetic.config('C1')
+        it = onb.agents.Infotaxis_Agent(agent.environment, thresholds=c['thresholds'])
+        it.initialize_state(n, onb.BeliefSet(it.model, _buffers=(bs._b.clone(), bs._scale.clone(), n), device=0))
+        ids_all = it.choose_action_device(return_delta_H=True).clone()
+        dh_all = it.last_delta_H.clone()
+        it.initialize_state(1200, onb.BeliefSet(it.model, _buffers=(bs._b[n - 1200:n].clone(), bs._scale[n - 1200:n].clone(), 1200), device=0))
+        ids_t = it.choose_action_device(return_delta_H=True)
+        np.testing.assert_allclose(dh_all[n - 1200:].cpu().numpy(), it.last_delta_H.cpu().numpy(), rtol=1e-4, atol=1e-5)
+        assert float((ids_all[n - 1200:] == ids_t).float().mean()) > 0.99
