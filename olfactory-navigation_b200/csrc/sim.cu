@@ -116,38 +116,64 @@ __global__ void sim_env_kernel(const olfnav_env e, const EnvArgs a) {
 }
 
 // Order-preserving compaction of the agents that did not reach the source: src_rows[j] = j-th such agent; counts[0] = m.
-// One CTA, tiles of 4096 flags.
-__global__ void __launch_bounds__(1024) sim_plan_kernel(int n, const unsigned char* __restrict__ reached, int* __restrict__ src_rows,
-                                                         int* __restrict__ counts) {
+// Two launches over tiles of 4096 flags (one CTA each): per-tile survivor counts, then every tile adds up the counts of the tiles
+// before it (a few hundred values at most), scans its own flags and scatters.  (A single-CTA scan took 53 us per step at 100 000
+// agents: 0.9 % of the step on the critical path between the environment step and the belief update.)
+__global__ void __launch_bounds__(1024) sim_plan_count_kernel(int n, const unsigned char* __restrict__ reached, int* __restrict__ tile_counts) {
     __shared__ int wsum[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 4096) {
-        const int i0 = base + 4 * threadIdx.x;
-        unsigned char f[4];
+    const int i0 = blockIdx.x * 4096 + 4 * threadIdx.x;
+    int mine = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = (i0 + k < n) ? (reached[i0 + k] ? 0 : 1) : 0;
-        const int mine = f[0] + f[1] + f[2] + f[3];
-        int v = mine;
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (lane == 31) wsum[w] = v;
-        __syncthreads();
-        if (w == 0) {
-            int s = wsum[lane];
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += u; }
-            wsum[lane] = s;
-        }
-        __syncthreads();
-        int off = carry + (w > 0 ? wsum[w - 1] : 0) + v - mine;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (f[k]) src_rows[off++] = i0 + k;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += wsum[31];
-        __syncthreads();
+    for (int k = 0; k < 4; ++k) mine += (i0 + k < n && !reached[i0 + k]) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) wsum[w] = mine;
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) tile_counts[blockIdx.x] = v;
     }
-    if (threadIdx.x == 0) { counts[0] = carry; counts[1] = 0; counts[2] = 0; counts[3] = n; }
+}
+
+__global__ void __launch_bounds__(1024) sim_plan_kernel(int n, const unsigned char* __restrict__ reached, const int* __restrict__ tile_counts,
+                                                         int* __restrict__ src_rows, int* __restrict__ counts) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // survivors in the tiles before this one (and, for the last tile, the total)
+    int before = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += 1024) before += tile_counts[j];
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) wsum[w] = before;
+    __syncthreads();
+    if (w == 0) {
+        int v = wsum[lane];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) base_s = v;
+    }
+    __syncthreads();
+    const int base = base_s;
+    const int i0 = blockIdx.x * 4096 + 4 * threadIdx.x;
+    unsigned char f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = (i0 + k < n) ? (reached[i0 + k] ? 0 : 1) : 0;
+    const int mine = f[0] + f[1] + f[2] + f[3];
+    int v = mine;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    __syncthreads();                       // wsum is reused
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int t = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+        wsum[lane] = t;
+    }
+    __syncthreads();
+    int off = base + (w > 0 ? wsum[w - 1] : 0) + v - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (f[k]) src_rows[off++] = i0 + k;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { counts[0] = base + wsum[31]; counts[1] = 0; counts[2] = 0; counts[3] = n; }
 }
 
 __global__ void sim_gather_kernel(int n, const int* __restrict__ counts, const int* __restrict__ src_rows, const int* __restrict__ act,
@@ -230,7 +256,16 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
     OLF_LAUNCH_CHECK();
 
     // 3. survivors and their compacted bookkeeping
-    sim_plan_kernel<<<1, 1024, 0, st>>>(n, a->rec_reached, a->src_rows, a->counts);
+    {
+        // per-tile counts live behind the compacted action ids (act_c holds n ints and is only written by the gather that follows...
+        // which runs after the plan): no extra scratch in the ABI
+        const int tiles = olf_div_up(n, 4096);
+        OLF_REQUIRE(tiles <= n, "sim_step: internal scratch");
+        int* tile_counts = a->act_c;
+        sim_plan_count_kernel<<<tiles, 1024, 0, st>>>(n, a->rec_reached, tile_counts);
+        sim_plan_kernel<<<tiles, 1024, 0, st>>>(n, a->rec_reached, tile_counts, a->src_rows, a->counts);
+        olf_count_launch(1);
+    }
     OLF_LAUNCH_CHECK();
     sim_gather_kernel<<<grid, 256, 0, st>>>(n, a->counts, a->src_rows, a->act, a->obs_id, a->rec_pos, (const long long*)a->ts_in,
                                             a->act_c, a->obs_c, a->pos_out, (long long*)a->ts_out);

@@ -260,3 +260,26 @@ def test_fused_step_run_equals_two_kernel_run(cfg, monkeypatch):
     _compare_runs(got, g)
     same = np.array(ref.done_at_step) == np.array(got.done_at_step)
     assert same.mean() > 0.97                      # near-ties of the value function may resolve differently (documented ties)
+
+
+def test_many_agents_compaction_across_plan_tiles():
+    '''
+    9 600 agents = 200 copies of the 48 golden start points (several 4 096-agent tiles of the compaction plan).  With every agent
+    on its own clock (reference_time_quirk off) the copies are independent, so each must reproduce the 48-agent run exactly, in order.
+    '''
+    import olfactory_navigation_b200 as onb
+    g = golden('runtest_fsvi_T1')
+    c = onb.synthetic.config('T1')
+    env = onb.Environment(**c['env_kwargs'])
+    env.reference_time_quirk = False
+    agent = onb.agents.PBVI_Agent(env, thresholds=c['thresholds'])
+    agent.value_function = onb.ValueFunction(agent.model, g['alphas'].astype(np.float64), g['alpha_actions'])
+    starts, tshift, horizon = g['start_points'].astype(int), g['time_shift'], int(g['horizon'])
+    kw = dict(horizon=horizon, print_progress=False, print_stats=False, batches=1)
+    one = onb.run_test(agent, n=len(starts), start_points=starts, time_shift=tshift, **kw)
+    reps = 200
+    many = onb.run_test(agent, n=reps * len(starts), start_points=np.tile(starts, (reps, 1)), time_shift=np.tile(tshift, reps), **kw)
+    assert np.array_equal(np.array(many.done_at_step), np.tile(np.array(one.done_at_step), reps))
+    assert np.array_equal(np.array(many.reached_source), np.tile(np.array(one.reached_source), reps))
+    pos_one, pos_many = np.array(one.positions), np.array(many.positions)
+    assert np.array_equal(pos_many, np.tile(pos_one, (1, reps, 1)))
