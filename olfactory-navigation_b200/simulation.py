@@ -284,6 +284,21 @@ def _run_batches(agent, n, start_points, time_shift, batches, **kw) -> Simulatio
     return combined
 
 
+_PINNED = {}
+
+
+def _pinned(name: str, nbytes: int) -> torch.Tensor:
+    '''
+    Page-locked host staging buffers are kept across run_test calls (grown on demand): cudaHostAlloc of a few MB costs milliseconds,
+    which is a visible fraction of a short run.  One set per process: run_test is not re-entrant on a device anyway.
+    '''
+    buf = _PINNED.get(name)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
+        _PINNED[name] = buf
+    return buf[:nbytes]
+
+
 def _run_single(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
                 reward_discount, distance_metric, print_progress, record: bool = True, timing: list = None) -> SimulationHistory:
     '''
@@ -337,7 +352,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     hist_t = i32(T + 1)
     eval_val, eval_idx = torch.empty(cap, dtype=torch.float32, device=dev), i32()
     counts = torch.zeros(4, dtype=torch.int32, device=dev)
-    counts_host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+    counts_host = _pinned('counts', 16).view(torch.int32)
+    counts_host.zero_()
     # two record sets so that step i+1 can run while step i's record is still being copied out
     # Record sets: ONE contiguous device buffer each (odor f64 | pos 2 x i32 | act i32 | reached u8 | term u8, 22 bytes per agent)
     # so that a step's record leaves the GPU as a single copy; two device sets (step i + 1 runs while step i's record is copied
@@ -354,7 +370,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     rec_bytes = 22 * cap
     rec_dev = [torch.empty(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     recs = [record_views(b) for b in rec_dev]
-    rec_host = [torch.empty(rec_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(3)] if record else []
+    rec_host = [_pinned(f'rec{k}', rec_bytes) for k in range(3)] if record else []
     rec_host_views = [record_views(b) for b in rec_host]
     rec_free = [None, None]            # event: the record set has been copied out
     pending = []
