@@ -324,10 +324,10 @@ def run_ours(args) -> None:
             'gpu_launches': launches, 'setup_ms_outside_value': setup_ms,
             'clocks': clk,
             'roofline': {'kernel': 'belief_step_tma_kernel<256>', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                         # ncu --set full, profiles/r1l_ncu_full_raw_belief_step_and_umma_ts.csv: dram read 12.352 GB + write 12.294 GB per launch of 100 000 rows
+                         # ncu --set full, profiles/r1q_ncu_full_raw_belief_step_and_umma_ts.csv: dram read 12.352 GB + write 12.292 GB per launch of 100 000 rows
                          # at 99 953 updated rows = 246 442 B per updated agent (algorithmic 246 344 B): scaled to this run's launches
-                         'traffic': 246459.5 * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if bs_bytes else None,
-                         'traffic_unit': 'bytes per launch (ncu r1l capture, scaled by updated rows)', 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
+                         'traffic': 246438.8 * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if bs_bytes else None,
+                         'traffic_unit': 'bytes per launch (ncu r1q capture, scaled by updated rows)', 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
                          'share_of_step': sum(bs_ms) / elapsed_ms, 'evaluate_ms_per_step': statistics.mean(ev_ms) if ev_ms else None,
                          'belief_step_ms_per_step': statistics.mean(bs_ms) if bs_ms else None},
         }
