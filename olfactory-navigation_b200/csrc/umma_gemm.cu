@@ -46,7 +46,7 @@ struct GemmParams {
                                  // wave share A and B tiles in L2 (a wave of 148 units = 148 / group_w m tiles x group_w n tiles)
     float* out_store;            // != NULL: store mode, out_store[row * out_ld + col] = product (col < rows_b); no max / argmax
     long long out_ld;
-    // Tail split (single n tile only): the tiles of the last, partial wave are cut along K into tail_split parts each, so that the
+    // Tail split: the units of the last, partial wave are cut along K into tail_split parts each, so that the
     // wave is spread over all SMs instead of costing a whole wave on a few (measured: evaluate of 100 000 rows = 5.28 waves ran
     // as long as 6 full waves).  Units [0, full_units) are whole tiles; unit full_units + t * tail_split + q is part q of tail tile t.
     // The parts' partial sums go to tail_ws[t][q][row][col] and are added in a fixed order by tail_finish_kernel (deterministic).
@@ -363,23 +363,42 @@ __global__ void segmax_decode_kernel(long long n, const unsigned long long* __re
     out_arg[i] = (int)(0xffffffffu - (unsigned)(k & 0xffffffffull));
 }
 
-// Tail tiles: add the K parts in a fixed order, then the same epilogue as the kernel (single n tile: one segment or plain store).
-__global__ void tail_finish_kernel(const GemmParams p, int BN, int tail_tiles) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // row inside the tail
-    if (i >= (long long)tail_tiles * BM) return;
-    const int t = (int)(i / BM), r = (int)(i - (long long)t * BM);
-    const long long row = (long long)(p.full_units + t) * BM + r;
+// Tail units: add the K parts in a fixed order, then the same epilogue as the kernel — plain store, one direct segment, or (several n
+// tiles) the running segmented max combined with atomicMax on the packed keys, exactly like the kernel's own flush.
+__global__ void tail_finish_kernel(const GemmParams p, int BN, int tail_units) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // (tail unit, row of the tile)
+    if (i >= (long long)tail_units * BM) return;
+    const int t = (int)(i / BM), rr = (int)(i - (long long)t * BM);
+    int mt, nt;
+    GemmParams q = p;
+    q.tail_split = 1;                                                             // decode a plain unit index
+    unit_to_tile(q, p.full_units + t, mt, nt);
+    const long long row = (long long)mt * BM + rr;
     if (row >= p.n_rows) return;
-    const float* w = p.tail_ws + ((long long)t * p.tail_split * BM + r) * BN;
+    const float* w = p.tail_ws + ((long long)t * p.tail_split * BM + rr) * BN;
+    const int col0 = nt * BN;
+    const bool direct = p.ws == nullptr;
+    int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;
     float best = -INFINITY;
     int best_idx = 0;
+    bool dirty = false;
     for (int j = 0; j < BN; ++j) {
         float x = 0.f;
-        for (int q = 0; q < p.tail_split; ++q) x += w[(long long)q * BM * BN + j];
-        if (p.out_store) { if (j < p.rows_b) p.out_store[row * p.out_ld + j] = x; }
-        else if (j < p.seg_len && x > best) { best = x; best_idx = j; }
+        for (int k = 0; k < p.tail_split; ++k) x += w[(long long)k * BM * BN + j];
+        if (p.out_store) { if (col0 + j < p.rows_b) p.out_store[row * p.out_ld + col0 + j] = x; continue; }
+        if (r < p.seg_len && cur_seg < p.n_seg) {
+            dirty = true;
+            if (x > best) { best = x; best_idx = r; }
+        }
+        if (++r == p.seg_stride) {
+            if (cur_seg < p.n_seg) {
+                if (direct) { p.out_val[row * p.n_seg + cur_seg] = best; p.out_arg[row * p.n_seg + cur_seg] = best_idx; }
+                else if (dirty) atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
+            }
+            r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
+        }
     }
-    if (!p.out_store) { p.out_val[row] = best; p.out_arg[row] = best_idx; }
+    if (!p.out_store && r != 0 && !direct && dirty && cur_seg < p.n_seg) atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -464,11 +483,11 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
 
     int grid = p.num_units < sm_count ? p.num_units : sm_count;
-    // tail split: single n tile (evaluate, infotaxis), more than one wave, last wave less than ~70 % full
+    // tail split: more than one wave of units and a last wave that is at most half full
     p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
     int tail_tiles = 0;
     static const bool tail_off = [] { const char* e = getenv("OLFNAV_GEMM_TAIL"); return e && e[0] == '0'; }();
-    if (!tail_off && p.num_n_tiles == 1 && p.n_seg == 1 && p.num_units > sm_count && p.num_k_blocks >= 64) {
+    if (!tail_off && p.num_units > sm_count && p.num_k_blocks >= 64) {
         const int tail = p.num_units % sm_count;
         const int split = tail ? (sm_count / tail < 4 ? sm_count / tail : 4) : 1;
         if (tail && split > 1) {

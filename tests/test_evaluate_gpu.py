@@ -210,3 +210,30 @@ def test_tail_split_of_the_last_wave(G):
         ids_t = it.choose_action_device(return_delta_H=True)
         np.testing.assert_allclose(dh_all[n - 1200:].cpu().numpy(), it.last_delta_H.cpu().numpy(), rtol=1e-4, atol=1e-5)
         assert float((ids_all[n - 1200:] == ids_t).float().mean()) > 0.99
+
+
+def test_tail_split_in_the_backup_gemm():
+    '''
+    Backup selection with several n tiles and a small last wave (896 points x 20 segments of 160 columns = 7 x 25 = 175 units on 148
+    SMs: the 27 tail units are cut along K): the tensor path must pick the same alpha per (belief, action, observation) as the FP32
+    SIMT path wherever the margin is clear, and the same best action / value.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(12)
+    B, G = 896, 150
+    bs = onb.BeliefSet(m, B)
+    for _ in range(4):
+        bs = bs.update(rng.integers(0, 4, B), np.zeros(B, dtype=int), raise_on_impossible_belief=False)
+    n = len(bs)
+    alphas = torch.as_tensor(np.abs(rng.standard_normal((G, m.padded_states))).astype(np.float32), device=bs._b.device)
+    H, W = m.grid_shape
+    alphas.view(G, H, -1)[:, :, W:] = 0
+    na2, a2, v2, g2 = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    na1, a1, v1, g1 = onb.solvers.backup_device(m, bs, alphas, 0.99, 1)
+    np.testing.assert_allclose(v2.cpu().numpy(), v1.cpu().numpy(), rtol=2e-5)
+    assert float((a2 == a1).float().mean()) > 0.995
+    assert float((g2 == g1).float().mean()) > 0.995
+    same = (a2 == a1) & (g2 == g1).flatten(1).all(1)
+    assert torch.equal(na2[same], na1[same])
