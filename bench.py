@@ -97,11 +97,25 @@ class ClockSampler:
 _CPU_SETUP = None
 
 
+def cpu_threads() -> int:
+    '''
+    Let the CPU arm use every host core: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin NumPy's BLAS to one
+    thread.  Returns the BLAS thread count actually in force (the oracle's element-wise NumPy passes are single-threaded by nature).
+    '''
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=os.cpu_count())
+        return max([int(i.get('num_threads', 1)) for i in threadpool_info()] or [1])
+    except Exception:
+        return 1
+
+
 def cpu_setup():
     'Oracle-side model of the same workload (NumPy fp64), built once.'
     global _CPU_SETUP
     if _CPU_SETUP is not None:
         return _CPU_SETUP
+    cpu_threads()
     from oracle import refloader
     refloader.install_oracle_toolkit()
     from oracle import sim
@@ -133,7 +147,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    cores = cpu_threads()
     alphas, actions = oracle_value_function()
     for _ in range(max(args.warmup, 0)):
         cpu_sample(alphas, actions, min(args.cpu_agents, 32), 2)
@@ -336,7 +350,7 @@ def run_ours(args) -> None:
         if not args.no_cpu_baseline and world == 1:
             vf = agent.value_function
             r = cpu_sample(vf.alpha_vector_array, vf.actions, args.cpu_agents, args.cpu_steps)
-            line['cpu_baseline'] = {'value': r['per_s'], 'unit': 'agent-steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+            line['cpu_baseline'] = {'value': r['per_s'], 'unit': 'agent-steps/s', 'cores': cpu_threads(), 'kind': 'port',
                                     'sample': f'oracle/sim.py (NumPy fp64 restatement of the reference loop) on {args.cpu_agents} agents x {args.cpu_steps} steps '
                                               f'of the same model and value function (G={G}); {r["agent_steps"]} agent-steps in {r["seconds"]:.1f} s; single process, BLAS threads'}
         print(json.dumps(line))
