@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 
 CONFIG = 'C2'
 N_AGENTS = 100_000
+WORKLOADS = {'C2': '55x247 plume + 14/62 margins = 83x371 = 30793 states, 4 actions, 3 observations, wrap_vertical',
+             'C5': '110x494 plume + 28/124 margins = 166x742 = 123172 states, 4 actions, 3 observations, wrap_vertical'}
 TRAIN = dict(expansions=10)          # the reference notebook's FSVI training call (experiments/pomdp_agent_training.ipynb cell 4)
 
 
@@ -43,14 +45,21 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--agents', type=int, default=N_AGENTS, help='agents per GPU (default: the BASELINE config)')
+    ap.add_argument('--agents', type=int, default=None, help='agents per GPU (default: 100 000 for C2, 125 000 for C5)')
+    ap.add_argument('--config', default='C2', choices=['C2', 'C5'],
+                    help='C2 = BASELINE configs[1] (the metric\'s configuration, default); C5 = configs[4], the 2x-resolution plume of the scaling sweep (10^6 agents over 8 GPUs)')
     ap.add_argument('--cpu-agents', type=int, default=256)
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-backup', action='store_true')
     ap.add_argument('--backup-points', type=int, default=10_000)
     ap.add_argument('--backup-alphas', type=int, default=512)
-    return ap.parse_args()
+    args = ap.parse_args()
+    global CONFIG
+    CONFIG = args.config
+    if args.agents is None:
+        args.agents = N_AGENTS if CONFIG == 'C2' else 125_000
+    return args
 
 
 def measured_peaks():
@@ -163,7 +172,7 @@ def run_reference(args) -> None:
     line = {'impl': 'reference', 'metric': 'agent_belief_steps_per_s', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_time / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'C2 run_test: 83x371 states, 4 actions, 3 observations, bounded CPU sample', 'agents_per_step': args.cpu_agents},
+            'config': {'workload': f'{CONFIG} run_test: ' + WORKLOADS[CONFIG] + ', bounded CPU sample', 'agents_per_step': args.cpu_agents},
             'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -330,7 +339,7 @@ def run_ours(args) -> None:
             'metric': 'agent_belief_steps_per_s', 'value': agent_steps / (elapsed_ms * 1e-3), 'unit': 'agent-steps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'C2 run_test of a trained FSVI agent: 55x247 plume + 14/62 margins = 83x371 = 30793 states, 4 actions, 3 observations, wrap_vertical',
+            'config': {'workload': f'{CONFIG} run_test of a trained FSVI agent: ' + WORKLOADS[CONFIG],
                        'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': 'simt-fp32' if G <= 8 else 'tcgen05-3xtf32',
                        'sharding': 'agents split across ranks, no data-path collective',
                        'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * model.padded_states * 4 / 1e9)},
