@@ -273,6 +273,32 @@ class PBVI_Agent(BeliefSimulationMixin, Agent):
         inst.saved_at = folder
         return inst
 
+    def generate_beliefs_from_trajectory(self, history, trajectory_i: int = 0, initial_belief: Belief = None) -> BeliefSet:
+        '''
+        The sequence of beliefs the agent goes through along one trajectory of a SimulationHistory (pbvi_agent.py:812-873):
+        replays (action, observation) of every recorded step with Belief.update, never as a goal observation; a failed update is
+        reported and skipped like in the reference.  Reads the history's arrays (the reference goes through its pandas frames).
+        '''
+        belief = Belief(self.model) if initial_belief is None else initial_belief
+        sequence = [belief]
+        done = int(history.done_at_step[trajectory_i])
+        steps = len(history) if done < 0 else done
+        action_set = np.asarray(self.action_set)
+        for t in range(steps):
+            vec = np.asarray(history.actions[t][trajectory_i])
+            a = int(np.argwhere(np.all(action_set == vec[None, :], axis=1))[0, 0])
+            o = [float(history.observations[t][trajectory_i])]
+            if self.space_aware:
+                o += [float(v) for v in history.positions[t][trajectory_i]]
+            obs = np.array([o]) if self.space_aware else np.array(o)
+            discrete_o = int(self.discretize_observations(observation=obs, action=vec[None, :], source_reached=np.array([False]))[0])
+            try:
+                belief = belief.update(a=a, o=discrete_o, use_reachability=self.use_reachability)
+                sequence.append(belief)
+            except Exception:
+                print(f'[Warning] Update of belief failed at step {t + 1}...')
+        return BeliefSet(self.model, sequence)
+
     def modify_environment(self, new_environment: Environment):
         '''
         A new agent on a modified environment; the alpha vectors are resampled to the new grid like the reference does

@@ -283,3 +283,35 @@ def test_many_agents_compaction_across_plan_tiles():
     assert np.array_equal(np.array(many.reached_source), np.tile(np.array(one.reached_source), reps))
     pos_one, pos_many = np.array(one.positions), np.array(many.positions)
     assert np.array_equal(pos_many, np.tile(pos_one, (1, reps, 1)))
+
+
+def test_generate_beliefs_from_trajectory():
+    'Replay of one recorded trajectory (reference pbvi_agent.py:812-873) == the oracle toolkit updating a single Belief step by step.'
+    import olfactory_navigation_b200 as onb
+    from conftest import oracle_model
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    g = golden('runtest_fsvi_T1')
+    env, _ = make('T1')
+    c = onb.synthetic.config('T1')
+    agent = onb.agents.PBVI_Agent(env, thresholds=c['thresholds'])
+    agent.value_function = onb.ValueFunction(agent.model, g['alphas'].astype(np.float64), g['alpha_actions'])
+    hist = onb.run_test(agent, n=len(g['start_points']), start_points=g['start_points'].astype(int), time_shift=g['time_shift'],
+                        horizon=int(g['horizon']), print_progress=False, print_stats=False, batches=1)
+    k = int(np.argmax(np.where(np.array(hist.done_at_step) < 0, len(hist), np.array(hist.done_at_step))))     # the longest trajectory
+    seq = agent.generate_beliefs_from_trajectory(hist, k)
+    steps = len(hist) if hist.done_at_step[k] < 0 else int(hist.done_at_step[k])
+    om = oracle_model(agent.model)
+    b = tk.Belief(om)
+    rows = [b.values]
+    for t in range(steps):
+        a = int(np.argwhere(np.all(agent.action_set == np.asarray(hist.actions[t][k])[None, :], axis=1))[0, 0])
+        o = int(agent.discretize_observations(np.array([hist.observations[t][k]]), np.asarray(hist.actions[t][k])[None, :], np.array([False]))[0])
+        try:
+            b = b.update(a=a, o=o)
+            rows.append(b.values)
+        except Exception:
+            pass
+    assert len(seq) == len(rows) and len(seq) >= 2
+    np.testing.assert_allclose(seq.belief_array, np.array(rows), rtol=2e-5, atol=1e-12)
