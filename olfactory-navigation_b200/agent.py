@@ -7,6 +7,12 @@ the model converters reject space-aware agents exactly like the reference's (env
 '''
 from __future__ import annotations
 
+import inspect
+import os
+import pickle
+import shutil
+import sys
+
 import numpy as np
 
 from .environment import Environment
@@ -152,6 +158,68 @@ class Agent:
             count = bins * cells
         ids[np.asarray(source_reached, dtype=bool)] = count
         return ids
+
+    # -- persistence (agent.py:488-567: pickle by default, subclasses store only what is needed) --
+    _transient = ('belief', '_bufs', '_alternate_version', 'action_played', 'succeeded_update', 'last_delta_H', '_action_ids')
+
+    def __getstate__(self):
+        'Simulation state (device buffers of the running agents) is never saved with the agent.'
+        state = self.__dict__.copy()
+        for key in self._transient:
+            if key in state:
+                state[key] = None
+        return state
+
+    def save(self, folder: str = None, force: bool = False, save_environment: bool = False) -> None:
+        folder = f'./Agent-{self.name}' if folder is None else folder + f'/Agent-{self.name}'
+        if not os.path.exists(folder):
+            os.mkdir(folder)
+        elif len(os.listdir(folder)) > 0:
+            if not force:
+                raise Exception(f'{folder} is not empty. If you want to overwrite the saved agent, enable "force".')
+            shutil.rmtree(folder)
+            os.mkdir(folder)
+        with open(folder + '/binary.pkl', 'wb') as f:
+            pickle.dump(self, f)
+        if save_environment:
+            self.environment.save(folder=(folder + f'/Env-{self.environment.name}'))
+        self.saved_at = os.path.abspath(folder)
+
+    @classmethod
+    def load(cls, folder: str) -> 'Agent':
+        'Dispatches to the subclass whose name appears in the folder name (agent.py:557-561), else unpickles.'
+        from . import agents
+        for name, obj in inspect.getmembers(agents):
+            if inspect.isclass(obj) and (name in folder) and issubclass(obj, cls) and (obj is not cls) and ('load' in obj.__dict__):
+                return obj.load(folder)
+        with open(folder + '/binary.pkl', 'rb') as f:
+            return pickle.load(f)
+
+    def modify_environment(self, new_environment: Environment) -> 'Agent':
+        'A new agent of the same class, thresholds and name on another environment (agent.py:569-593).'
+        return self.__class__(environment=new_environment, thresholds=self.thresholds, name=self.name)
+
+    def size_on_memory(self) -> int:
+        'Bytes held by the agent and its components, host arrays and device tensors alike (agent.py:656-667).'
+        seen, total, stack = set(), 0, [self]
+        while stack:
+            obj = stack.pop()
+            if id(obj) in seen:
+                continue
+            seen.add(id(obj))
+            if isinstance(obj, np.ndarray):
+                total += obj.nbytes
+            elif hasattr(obj, 'element_size') and hasattr(obj, 'nelement'):
+                total += obj.element_size() * obj.nelement()
+            else:
+                total += sys.getsizeof(obj)
+                if isinstance(obj, dict):
+                    stack.extend(obj.values())
+                elif isinstance(obj, (list, tuple, set)):
+                    stack.extend(obj)
+                elif hasattr(obj, '__dict__') and not inspect.ismodule(obj) and not inspect.isclass(obj):
+                    stack.extend(v for k, v in vars(obj).items() if k != '_alternate_version')
+        return total
 
     @property
     def movement_set(self) -> np.ndarray:

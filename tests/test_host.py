@@ -125,3 +125,23 @@ def test_against_live_reference_when_available():
         assert ragent.name == agent.name
         assert np.array_equal(ragent.model.observation_table, agent.model.observation_table)
         assert np.array_equal(ragent.model.reachable_states, agent.model.reachable_states)
+
+
+def test_base_agent_persistence(tmp_path):
+    'Base Agent.save/load/modify_environment/size_on_memory (reference agent.py:488-667): pickle by default, subclass dispatch by folder name.'
+    import olfactory_navigation_b200 as onb
+    env, _ = make('T0')
+    ag = onb.agents.Infotaxis_Agent(env, thresholds=[0.2, 0.7])
+    ag.save(folder=str(tmp_path))
+    folder = str(tmp_path / f'Agent-{ag.name}')
+    with pytest.raises(Exception):
+        ag.save(folder=str(tmp_path))                       # not empty, no force
+    ag.save(folder=str(tmp_path), force=True)
+    back = onb.Agent.load(folder)
+    assert type(back) is onb.agents.Infotaxis_Agent and back.name == ag.name
+    assert np.array_equal(back.thresholds, ag.thresholds)
+    assert np.array_equal(back.model.observation_table, ag.model.observation_table)
+    env2, _ = make('T1')
+    moved = ag.modify_environment(env2)
+    assert type(moved) is type(ag) and moved.environment is env2 and np.array_equal(moved.thresholds, ag.thresholds)
+    assert ag.size_on_memory() > ag.model.observation_table.nbytes
