@@ -145,10 +145,11 @@ def cpu_sample(alphas: np.ndarray, actions: np.ndarray, n: int, steps: int, seed
 
 
 def oracle_value_function(G_target: int = None):
-    'A value function for the reference arm without a GPU: the oracle\'s own VI (QMDP alphas, G = 4).'
+    'The value function of the reference arm, trained without a GPU: the oracle\'s own FSVI with the bench\'s training call (untimed setup).'
     sim, setup = cpu_setup()
     import pomdp_toolkit as tk
-    vf, _ = tk.solvers.VI.solve(setup['model'], horizon=1000, gamma=0.99, eps=1e-6)
+    import olfactory_navigation_b200.synthetic as syn
+    vf = tk.solvers.FSVI.solve(setup['model'], gamma=0.99, eps=1e-6, rng=np.random.default_rng(syn.SEED), print_progress=False, **TRAIN)[0]
     return vf.alpha_vector_array, vf.actions
 
 
@@ -167,12 +168,13 @@ def run_reference(args) -> None:
         total_time += r['seconds']
     value = total_steps / total_time
     sample = (f'oracle/sim.py NumPy fp64 restatement of the reference loop (reference = pure Python over the absent pomdp_toolkit); '
-              f'{args.cpu_agents} agents x {args.cpu_steps} sim steps per bench step on the {CONFIG} model, QMDP value function (G=4), '
+              f'{args.cpu_agents} agents x {args.cpu_steps} sim steps per bench step on the {CONFIG} model, FSVI value function trained by the oracle (expansions=10, G={len(alphas)}), '
               f'single process, NumPy/BLAS threads')
     line = {'impl': 'reference', 'metric': 'agent_belief_steps_per_s', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total_time / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG} run_test: ' + WORKLOADS[CONFIG] + ', bounded CPU sample', 'agents_per_step': args.cpu_agents},
+            'config': {'workload': f'{CONFIG} run_test of a trained FSVI agent: ' + WORKLOADS[CONFIG] + ', bounded CPU sample', 'agents_per_step': args.cpu_agents,
+                       'alpha_vectors': int(len(alphas))},
             'cpu_baseline': {'value': value, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
