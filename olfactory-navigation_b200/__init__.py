@@ -20,3 +20,4 @@ from . import agents                                  # noqa: F401
 from .converter import exact_converter, minimal_converter   # noqa: F401
 from .simulation import run_test, SimulationHistory   # noqa: F401
 from . import synthetic                               # noqa: F401
+from . import test_setups                             # noqa: F401

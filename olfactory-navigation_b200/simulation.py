@@ -8,13 +8,14 @@ stays on the GPU: positions, time shifts and beliefs never leave HBM; per step o
 (action id, position, odor, flags) is copied to pinned host memory, asynchronously, on a side
 stream.  Host <-> device boundary: start points / time shifts in (once), records out (per step).
 
-Analysis DataFrames, CSV save/load and plots of the reference's SimulationHistory are host-side
-bookkeeping outside the hot path and are not rebuilt here.
+The data format on the far side of the path — the per-run / general analysis tables and the CSV file a history is saved to
+and loaded from (simulation.py:259-386, :492-548, :621-997) — is kept column for column, so files written here load in the
+reference and vice versa.  Plots are not rebuilt.
 '''
 from __future__ import annotations
 
 import math
-from datetime import datetime
+from datetime import datetime, timedelta
 
 import os
 
@@ -54,6 +55,7 @@ class SimulationHistory:
         self._running_sims = np.arange(self.n)
         self._steps = []          # compact records: (sim ids, action ids, positions, observations)
         self._dense = None
+        self._simulation_dfs = None
         self.environment_dimensions = environment.dimensions
         self.environment_shape = environment.shape
         self.environment_source_position = environment.source_position
@@ -65,6 +67,7 @@ class SimulationHistory:
                  reached_source: np.ndarray, interupt: np.ndarray, action_is_id: bool = False) -> None:
         'Same contract as the reference\'s add_step (simulation.py:168-227); arrays cover the running simulations.'
         self._dense = None
+        self._simulation_dfs = None
         self.timestamps[0].append(datetime.now())
         sims = self._running_sims
         self._steps.append((sims, np.asarray(actions), np.asarray(next_positions), np.asarray(observations, dtype=float), action_is_id))
@@ -192,8 +195,256 @@ class SimulationHistory:
                 assert i1 == i2
                 steps.append((np.concatenate([s1, s2]), np.concatenate([a1, a2]), np.concatenate([p1, p2]), np.concatenate([o1, o2]), i1))
         out._steps = steps
-        out.timestamps = {0: self.timestamps[0], 1: other.timestamps[0]}
+        out.timestamps = {**self.timestamps, **{k + self.n: v for k, v in other.timestamps.items()}}    # keyed by the first run of each batch
         return out
+
+    # -- analysis tables (simulation.py:259-386) -------------------------------------------------
+    @property
+    def _axes_labels(self) -> list:
+        d = self.environment_dimensions
+        return ['z', 'y', 'x'][-d:] if d <= 3 else [f'x{i}' for i in range(d)]
+
+    def _batches(self):
+        'Yields (first run, one past the last run, seconds since the batch started at the end of every step).'
+        bounds = sorted(self.timestamps.keys()) + [self.n]
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            ts = self.timestamps[lo]
+            yield lo, hi, np.array([(t - ts[0]).total_seconds() for t in ts[1:]])
+
+    @property
+    def start_time(self) -> datetime:
+        return self.timestamps[0][0]
+
+    @property
+    def runs_analysis_df(self):
+        'One row per run: start point, optimal step count, outcome, steps, discounted reward, extra steps, Tmin/T, wall time.'
+        import pandas as pd
+        run_times = np.zeros(self.n)
+        for lo, hi, cum in self._batches():
+            end = self.done_at_step[lo:hi]
+            run_times[lo:hi] = cum[np.where(end > 0, end - 1, end)] if len(cum) else 0.0
+        df = pd.DataFrame(self.start_points, columns=self._axes_labels)
+        df['optimal_steps_count'] = self.compute_distance_to_source()
+        df['converged'] = self.reached_source
+        df['encountered_error'] = self.error_simulations
+        df['steps_taken'] = self.steps_taken
+        df['discounted_rewards'] = self.reward_discount ** df['steps_taken']
+        df['extra_steps'] = df['steps_taken'] - df['optimal_steps_count']
+        df['t_min_over_t'] = df['optimal_steps_count'] / df['steps_taken']
+        df['time_s'] = run_times
+        df['time_per_it_s'] = df['time_s'] / df['steps_taken']
+        df.index = [f'run_{i}' for i in range(self.n)]
+        return df
+
+    @property
+    def general_analysis_df(self):
+        'mean / standard deviation over all runs and over the successful ones, run counts, and the two time-per-step figures.'
+        import pandas as pd
+        runs = self.runs_analysis_df
+        cols = ['converged', 'encountered_error', 'steps_taken', 'discounted_rewards', 'extra_steps', 't_min_over_t', 'time_s', 'time_per_it_s']
+        ok = runs.loc[runs['converged'], cols]
+        out = pd.DataFrame([runs[cols].mean(), runs[cols].std(), ok.mean(), ok.std()],
+                           index=['mean', 'standard_deviation', 'success_mean', 'success_standard_deviation'], columns=cols).astype(object)
+        out.loc[['standard_deviation', 'success_mean', 'success_standard_deviation'], ['converged', 'encountered_error']] = None
+        out.insert(0, 'count', [self.n, None, self.success_count, None])
+        # seconds per agent-step until the first agent of each batch is done (t1) and until the last one is (t2);
+        # both are divided by the t1 step count, like the reference does (simulation.py:377-378)
+        time_t1 = time_t2 = 0.0
+        steps_t1 = 0
+        for lo, hi, cum in self._batches():
+            end = self.done_at_step[lo:hi]
+            end = np.where(end > 0, end, self.horizon)
+            time_t1 += cum[end.min() - 1]
+            time_t2 += cum[end.max() - 1]
+            steps_t1 += (hi - lo) * int(end.min())
+        out['delta_t1_s'] = [time_t1 / steps_t1, None, None, None]
+        out['delta_t2_s'] = [time_t2 / steps_t1, None, None, None]
+        return out
+
+    # -- per-run tables and the CSV format (simulation.py:492-548, :621-997) -----------------------
+    @property
+    def simulation_dfs(self) -> list:
+        '''
+        One table per run: row 0 is the start (time shift, start point, nothing else), row k the k-th step
+        (time, position reached, action vector played, odor observed, 1 on the row where the source was reached).
+        '''
+        import pandas as pd
+        if getattr(self, '_simulation_dfs', None) is not None:
+            return self._simulation_dfs
+        pos, act, obs = np.array(self.positions), np.array(self.actions), np.array(self.observations)
+        axes = self._axes_labels
+        layered = self.environment_layer_labels is not None
+        dfs = []
+        for i in range(self.n):
+            length = int(self.done_at_step[i]) if self.done_at_step[i] >= 0 else len(pos)
+            col = {'time': np.arange(length + 1) + self.time_shift[i]}
+            for k, axis in enumerate(axes):
+                col[axis] = np.hstack([self.start_points[i, k], pos[:length, i, k]]) if length else np.array([self.start_points[i, k]])
+            if layered:
+                col['layer'] = np.hstack([[None], act[:length, i, 0]]) if length else np.array([None])
+            for k, axis in enumerate(axes):
+                col['d' + axis] = np.hstack([[None], act[:length, i, k + (1 if layered else 0)]]) if length else np.array([None])
+            col['o'] = np.hstack([[None], obs[:length, i]]) if length else np.array([None])
+            col['reached_source'] = np.hstack([[None], np.where(np.arange(1, length + 1) == self.done_at_step[i], int(self.reached_source[i]), 0)])
+            dfs.append(pd.DataFrame(col))
+        self._simulation_dfs = dfs
+        return dfs
+
+    def save(self, file: str = None, folder: str = None, save_analysis: bool = True, save_components: bool = False) -> None:
+        '''
+        One CSV with every run stacked, the step timestamps of each batch, and a property / property_value column pair with
+        what is needed to rebuild the history (same columns and property names as simulation.py:621-740).
+        '''
+        import pandas as pd
+        assert (self.environment is not None) and (self.agent is not None), 'Function not available, the agent and/or the environment is not set.'
+        if file is None:
+            shape = '_'.join(str(v) for v in self.environment_shape)
+            file = f'Simulations-s_{shape}-n_{self.n}-{self.start_time.strftime("%Y%m%d_%H%M%S")}-horizon_{self.horizon}.csv'
+        if not file.endswith('.csv'):
+            file += '.csv'
+        folder = './' if folder is None else folder
+        if '/' not in folder:
+            folder = './' + folder
+        if not os.path.exists(folder):
+            os.mkdir(folder)
+        if not folder.endswith('/'):
+            folder += '/'
+        if save_components:
+            if (self.environment.saved_at is None) or (folder not in self.environment.saved_at):
+                self.environment.save(folder=folder)
+            if (self.agent.saved_at is None) or (folder not in self.agent.saved_at):
+                self.agent.save(folder=folder)
+
+        dfs = self.simulation_dfs
+        table = pd.concat(dfs)
+        first_row = np.concatenate([[0], np.cumsum([len(d) for d in dfs])])
+        stamps = [None] * len(table)
+        for run, ts in self.timestamps.items():
+            for k, t in enumerate(ts):
+                if first_row[run] + k < len(stamps):
+                    stamps[first_row[run] + k] = t.strftime('%Y%m%d_%H%M%S%f') if k == 0 else t.strftime('%H%M%S%f')
+        table['timestamps'] = stamps
+        thr = np.asarray(self.agent_thresholds)
+        thr_text = '&'.join('_'.join(str(v) for v in row) for row in thr[:, 1:-1]) if thr.ndim == 2 else '_'.join(str(v) for v in thr)
+        props = {'horizon': str(self.horizon), 'reward_discount': str(self.reward_discount), 'distance_metric': self.distance_metric,
+                 'used_gpu': str(self.used_gpu), 'environment_name': self.environment.name, 'environment_saved_at': self.environment.saved_at,
+                 'environment_dimensions': str(self.environment_dimensions),
+                 'environment_shape': '_'.join(str(v) for v in self.environment_shape),
+                 'environment_source_position': '_'.join(str(v) for v in self.environment_source_position),
+                 'environment_source_radius': str(self.environment_source_radius),
+                 'environment_layer_labels': '' if self.environment_layer_labels is None else '&'.join(self.environment_layer_labels),
+                 'agent_name': self.agent.name, 'agent_class_name': self.agent.class_name, 'agent_saved_at': self.agent.saved_at,
+                 'agent_thresholds': thr_text}
+        assert len(table) >= len(props), 'the history is too short to carry its property rows'
+        pad = [None] * (len(table) - len(props))
+        table['property'] = list(props.keys()) + pad
+        table['property_value'] = list(props.values()) + pad
+        table.to_csv(folder + file, index=False)
+        print(f'Simulations saved to: {folder + file}')
+        if save_analysis:
+            self.runs_analysis_df.to_csv(folder + file.replace('.csv', '-runs_analysis.csv'))
+            self.general_analysis_df.to_csv(folder + file.replace('.csv', '-general_analysis.csv'))
+            print(f"Simulation's analysis saved to: {folder + file.replace('.csv', '-[runs|general]_analysis.csv')}")
+
+    @classmethod
+    def load_from_file(cls, file: str, environment=False, agent=False) -> 'SimulationHistory':
+        return cls.load(file, environment, agent)
+
+    @classmethod
+    def load(cls, file: str, environment=False, agent=False) -> 'SimulationHistory':
+        '''
+        Rebuilds a history from the CSV written by `save` (here or by the reference, simulation.py:752-997; the pre-property
+        "legacy" layout is not read).  `environment` / `agent`: an instance, or True to load them from the recorded paths.
+        '''
+        import pandas as pd
+        with open(file, 'r') as f:
+            columns = f.readline().strip().split(',')
+        dtypes = {c: float for c in columns}
+        dtypes.update(time=int, timestamps=str, property=str, property_value=str)
+        if 'layer' in columns:
+            dtypes['layer'] = float            # empty on the start rows
+        table = pd.read_csv(file, dtype=dtypes)
+        props = {}
+        for name, value in zip(table['property'], table['property_value']):
+            if not isinstance(name, str):
+                break
+            props[name] = value
+        horizon = int(props['horizon'])
+
+        def recorded(path) -> bool:
+            return isinstance(path, str) and len(path) > 0
+        if environment is True:
+            assert recorded(props.get('environment_saved_at')), \
+                'Environment was not saved at the time of the saving of the simulation history. Input an environment to the environment parameter or toggle the parameter to False.'
+            environment = Environment.load(props['environment_saved_at'])
+        if agent is True:
+            assert recorded(props.get('agent_saved_at')), \
+                'Agent was not saved at the time of the saving of the simulation history. Input an agent to the agent parameter or toggle the parameter to False.'
+            agent = Agent.load(props['agent_saved_at'])
+
+        data_cols = [c for c in columns if c not in ('property', 'property_value')]
+        layered = ((len(data_cols) - 4) % 2) == 1          # time, o, reached_source, timestamps + 2 per axis (+ layer)
+        dims = (len(data_cols) - 4) // 2
+        num_cols = [c for c in data_cols if c != 'timestamps']
+        starts = np.flatnonzero(table['reached_source'].isnull().to_numpy())
+        values = table[num_cols].to_numpy(dtype=float)
+        runs = np.split(values, starts[1:])
+        sizes = np.array([len(r) for r in runs])
+        n, steps = len(runs), int(sizes.max()) - 1
+        cube = np.full((steps + 1, n, len(num_cols)), -1.0)
+        for i, r in enumerate(runs):
+            cube[:len(r), i] = r
+        a0 = 1 + dims
+        a1 = a0 + (1 if layered else 0) + dims
+
+        hist = cls.__new__(cls)
+        hist.n = n
+        hist.environment = environment if isinstance(environment, Environment) else None
+        hist.agent = agent if isinstance(agent, Agent) else None
+        hist.time_shift = cube[0, :, 0].astype(int)
+        hist.horizon = horizon
+        hist.reward_discount = float(props['reward_discount'])
+        hist.distance_metric = props['distance_metric']
+        hist.used_gpu = props['used_gpu'] == 'True'
+        hist.start_points = cube[0, :, 1:a0].astype(int)
+        hist.reached_source = np.array([r[-1, -1] == 1 for r in runs])
+        hist.done_at_step = np.where((sizes - 1 < horizon) | hist.reached_source, sizes - 1, -1)    # a run that reached the source on the horizon step is done too
+        hist._running_sims = np.flatnonzero(hist.done_at_step < 0)
+        hist._steps = [None] * steps
+        hist._dense = ([cube[k, :, a0:a1].astype(int) for k in range(1, steps + 1)],
+                       [cube[k, :, 1:a0].astype(int) for k in range(1, steps + 1)],
+                       [cube[k, :, a1] for k in range(1, steps + 1)])
+        hist._simulation_dfs = [pd.DataFrame(r, columns=num_cols) for r in runs]
+
+        # step timestamps: a full date on the first row of every batch, time of day afterwards (a smaller value = next day)
+        hist.timestamps = {}
+        stamp = table['timestamps']
+        heads = [k for k, v in enumerate(stamp) if isinstance(v, str) and '_' in v]
+        for lo, hi in zip(heads, heads[1:] + [len(stamp)]):
+            group = [v for v in stamp[lo:hi] if isinstance(v, str)]
+            ts = [datetime.strptime(group[0], '%Y%m%d_%H%M%S%f')]
+            day = group[0][:9]
+            shift = timedelta(days=0)
+            for text in group[1:]:
+                t = datetime.strptime(day + text, '%Y%m%d_%H%M%S%f') + shift
+                if t < ts[-1]:
+                    shift += timedelta(days=1)
+                    t += timedelta(days=1)
+                ts.append(t)
+            hist.timestamps[int(np.flatnonzero(starts == lo)[0])] = ts
+        if len(hist.timestamps) == 0:
+            print('[Warning] No timestamps were found in the loaded simulation history...')
+
+        hist.environment_dimensions = int(props['environment_dimensions'])
+        hist.environment_shape = tuple(int(v) for v in str(props['environment_shape']).split('_'))
+        hist.environment_source_position = np.array([float(v) for v in str(props['environment_source_position']).split('_')])
+        hist.environment_source_radius = float(props['environment_source_radius'])
+        labels = props.get('environment_layer_labels')
+        hist.environment_layer_labels = labels.split('&') if isinstance(labels, str) and len(labels) > 0 else None
+        text = props['agent_thresholds']
+        hist.agent_thresholds = (np.array([np.array(row.split('_')).astype(float) for row in text.split('&')]) if '&' in text
+                                 else np.array(text.split('_')).astype(float))
+        return hist
 
 
 def run_test(agent: Agent,
