@@ -151,26 +151,20 @@ class SimulationHistory:
 
     @property
     def summary(self) -> str:
-        steps = self.steps_taken.astype(float)
-        ok = self.reached_source
-        n_ok = int(np.sum(ok))
-        fails = self.n - n_ok
-        s = f'Simulations reached goal: {n_ok}/{self.n} ({fails} failures (reached horizon: {int(np.sum(self.simulations_at_horizon))})) ({100.0 * n_ok / self.n:.2f}% success)\n'
-        if self.error_count:
-            s += f' - Simulations with errors: {self.error_count}\n'
-        dist = np.maximum(self.compute_distance_to_source(), 0.0)
-        adr = np.where(ok, self.reward_discount ** steps, 0.0)
-        with np.errstate(divide='ignore', invalid='ignore'):
-            ratio = np.where(steps > 0, dist / steps, 0.0)
-
-        def ms(x, sel=None):
-            x = x if sel is None else x[sel]
-            return (float(np.mean(x)), float(np.std(x))) if len(x) else (float('nan'), float('nan'))
-        for label, arr in (('Average step count:', steps), ('Extra steps:', steps - dist),
-                           ('Average discounted rewards (ADR):', adr), ('Tmin/T:', ratio)):
-            a, b = ms(arr), ms(arr, ok)
-            s += f' - {label:<38}{a[0]:.3f} +- {a[1]:.2f} (Successful only: {b[0]:.3f} +- {b[1]:.2f})\n'
-        return s
+        'Success count and mean +- standard deviation of the run metrics, all runs and successful ones (simulation.py:438-481).'
+        n_ok = self.success_count
+        text = f'Simulations reached goal: {n_ok}/{self.n} ({(n_ok * 100) / self.n:.2f}% success)'
+        if self.error_count > 0:
+            text += f' - {self.error_count} AGENTS ENCOUNTERED ERRORS'
+        if n_ok == 0:
+            return text
+        df = self.general_analysis_df
+        for label, col in (('Average step count:', 'steps_taken'), ('Extra steps:', 'extra_steps'),
+                           ('Average discounted rewards (ADR):', 'discounted_rewards'), ('Tmin/T:', 't_min_over_t'),
+                           ('Average time to completion (s):', 'time_s'), ('Average time per iteration (s):', 'time_per_it_s')):
+            v = [float(df.loc[row, col]) for row in ('mean', 'standard_deviation', 'success_mean', 'success_standard_deviation')]
+            text += f"\n - {label:<35} {v[0]:.3f} +- {v[1]:.2f} (Successful only: {v[2]:.3f} +- {v[3]:.2f})"
+        return text
 
     def __add__(self, other: 'SimulationHistory') -> 'SimulationHistory':
         'Concatenate two batches (simulation.py:550-618).'
@@ -254,8 +248,9 @@ class SimulationHistory:
         for lo, hi, cum in self._batches():
             end = self.done_at_step[lo:hi]
             end = np.where(end > 0, end, self.horizon)
-            time_t1 += cum[end.min() - 1]
-            time_t2 += cum[end.max() - 1]
+            last = len(cum) - 1                               # (a history cut short of its horizon has fewer timestamps)
+            time_t1 += cum[min(end.min() - 1, last)] if len(cum) else 0.0
+            time_t2 += cum[min(end.max() - 1, last)] if len(cum) else 0.0
             steps_t1 += (hi - lo) * int(end.min())
         out['delta_t1_s'] = [time_t1 / steps_t1, None, None, None]
         out['delta_t2_s'] = [time_t2 / steps_t1, None, None, None]

@@ -27,6 +27,7 @@ def test_history_files_match_the_reference(tmp_path):
     g = golden('history_T0')
     both = _both()
     assert np.array_equal(both.done_at_step, g['done_at_step']) and np.array_equal(both.reached_source, g['reached_source'])
+    assert both.summary == str(g['summary'][()])
     both.save(file='hist', folder=str(tmp_path))
     for key, name in (('csv', 'hist.csv'), ('runs_analysis', 'hist-runs_analysis.csv'), ('general_analysis', 'hist-general_analysis.csv')):
         mine = pd.read_csv(tmp_path / name)
