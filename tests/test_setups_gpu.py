@@ -76,3 +76,15 @@ def test_scale_and_shape_robustness_files(trained, tmp_path):
     assert len(hists) == len(table) and set(table['y_multiplier']) <= {80, 100}
     assert all(os.path.exists(f'{folder}/test_env_y-{y}_x-{x}.csv') for y, x in zip(table['y_multiplier'], table['x_multiplier']))
     assert all(h.environment.shape == env.shape for h in hists)               # the plume is stretched inside the same grid
+
+
+def test_run_test_prints_the_reference_summary(trained, capsys):
+    import olfactory_navigation_b200 as onb
+    env, agent = trained
+    hist = onb.run_test(agent, n=50, horizon=80, print_progress=False, print_stats=True, batches=2)
+    out = capsys.readouterr().out
+    assert f'Simulations reached goal: {hist.success_count}/50' in out and 'Average discounted rewards (ADR):' in out
+    assert sorted(hist.timestamps) == [0, 25]                                  # one timestamp list per batch, keyed by its first run
+    runs = hist.runs_analysis_df
+    assert np.array_equal(runs['steps_taken'], hist.steps_taken) and np.all(runs['time_s'] > 0)
+    assert float(hist.general_analysis_df.loc['mean', 'delta_t1_s']) > 0
