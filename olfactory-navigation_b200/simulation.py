@@ -341,6 +341,23 @@ class SimulationHistory:
             self.general_analysis_df.to_csv(folder + file.replace('.csv', '-general_analysis.csv'))
             print(f"Simulation's analysis saved to: {folder + file.replace('.csv', '-[runs|general]_analysis.csv')}")
 
+    def compare(self, *other: 'SimulationHistory'):
+        return self.__class__.compare_all(self, *other)
+
+    @classmethod
+    def compare_all(cls, *simulation_histories: 'SimulationHistory'):
+        'One row per history: mean / std of the run metrics over all runs and over the successful ones (simulation.py:999-1047).'
+        import pandas as pd
+        rows = []
+        for hist in simulation_histories:
+            df = hist.general_analysis_df
+            row = {'convergence': df.loc['mean', 'converged'], 'convergence_std': df.loc['standard_deviation', 'converged']}
+            for col in ('steps_taken', 'discounted_rewards', 'extra_steps', 't_min_over_t'):
+                for suffix, line in (('', 'mean'), ('_std', 'standard_deviation'), ('_success', 'success_mean'), ('_success_std', 'success_standard_deviation')):
+                    row[col + suffix] = df.loc[line, col]
+            rows.append(row)
+        return pd.DataFrame(rows)
+
     @classmethod
     def load_from_file(cls, file: str, environment=False, agent=False) -> 'SimulationHistory':
         return cls.load(file, environment, agent)

@@ -1,6 +1,7 @@
 '''
 Test set-ups built on run_test — the callers of the hot path the reference ships in `olfactory_navigation/test_setups.py`
-(:24-115 all start points, :117-232 n per cell, :287-462 shape robustness, :517-687 scale robustness).  Same names, arguments
+(:24-115 all start points, :117-232 n per cell, :287-462 shape robustness, :517-687 scale robustness, :689-820 agents x
+environments comparison, :1073-1166 void environment).  Same names, arguments
 and outputs (list of SimulationHistory, CSV files, `_analysis.csv`); every simulation runs on the device through run_test.
 '''
 from __future__ import annotations
@@ -146,6 +147,59 @@ def test_scale_robustness(agent: Agent, environment: Environment = None, step_pe
     return histories
 
 
+def test_agent_in_void(agent: Agent, **run_test_kwargs) -> SimulationHistory:
+    '''
+    One trajectory in a copy of the agent's environment whose odor data is all zero, from the start cell farthest (manhattan) from
+    the source (test_setups.py:1073-1166).  The remaining keyword arguments go to run_test.
+    '''
+    assert agent.trained, 'Agent must be trained...'
+    void = agent.environment.modify()
+    void._data = np.zeros_like(void.data)
+    void.data_processed = True
+    void._device_handles = {}                      # nothing uploaded yet; the device copy is made from the zeroed frames
+    starts = np.argwhere(void.start_probabilities > 0)
+    if len(starts) == 0:
+        raise ValueError('No valid starting positions are available in the void environment.')
+    far = starts[int(np.argmax(void.distance_to_source(starts, metric='manhattan')))]
+    return run_test(agent=agent, n=1, start_points=far[None, :], environment=void, **run_test_kwargs)
+
+
+def test_agents(*agents: Agent, environments: list[Environment], initialization_values: list[dict] = None, print_progress: bool = False,
+                save_histories_path: str = None, save_result_table: bool = True, **run_test_kwargs):
+    '''
+    Every trained agent on every environment from every start cell; returns the comparison table (SimulationHistory.compare_all
+    per agent, stacked under an `agent` index level) and optionally saves the histories and the table (test_setups.py:689-820).
+    '''
+    import pandas as pd
+    initialization_values = [{}] * len(agents) if initialization_values is None else initialization_values
+    tables, names = [], []
+    for i_agent, (agent, init) in enumerate(zip(agents, initialization_values)):
+        print(f'Testing Agent {i_agent}:')
+        if not agent.trained:
+            print(f'[Warning] Skipping agent {i_agent} due to it not being marked as trained...')
+            continue
+        histories = []
+        for i_env, environment in enumerate(environments):
+            print(f'- Environment {i_env}')
+            hist = run_all_starts_test(agent=agent, environment=environment, initialization_values=init, print_progress=print_progress,
+                                       **run_test_kwargs)
+            histories.append(hist)
+            if save_histories_path is not None:
+                hist.save(file=f'Simualtions-agent_{i_agent}-environment_{i_env}', folder=save_histories_path, save_analysis=False)
+        table = SimulationHistory.compare_all(*histories)
+        table['environment'] = [f'environment_{i}' for i in range(len(environments))]
+        tables.append(table)
+        names.append(f'agent_{i_agent}')
+        print('--------------------------------------')
+    comparison = pd.concat(tables, keys=names, names=['agent'])
+    if save_result_table:
+        folder = './' if save_histories_path is None else save_histories_path
+        comparison.to_csv(os.path.join(folder, 'Simulation_comparison-' + datetime.now().strftime('%Y%m%d_%H%M%S%f')))
+    return comparison
+
+
 # not collected as tests when the module is imported from a test file
+test_agents.__test__ = False
+test_agent_in_void.__test__ = False
 test_shape_robustness.__test__ = False
 test_scale_robustness.__test__ = False

@@ -42,6 +42,8 @@ if __name__ == '__main__':
     both.save(file='hist', folder=d, save_analysis=True)
     out = {name: np.array(open(os.path.join(d, f)).read()) for name, f in
            (('csv', 'hist.csv'), ('runs_analysis', 'hist-runs_analysis.csv'), ('general_analysis', 'hist-general_analysis.csv'))}
+    # (the reference's table cells are one-element Series — its analysis table has a one-level MultiIndex; the numbers are frozen)
+    out['compare'] = np.array(both.compare(ha, hb).map(lambda v: float(np.asarray(v).ravel()[0])).to_csv(index=False))
     out.update(summary=np.array(both.summary), done_at_step=both.done_at_step, reached_source=both.reached_source, n_steps=np.array(len(both.positions)))
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'history_T0.npz'), **out)
     print(out['csv'][()][:1500])

@@ -13,14 +13,23 @@ from conftest import golden, make
 from history_feed import feed, STARTS_A, STARTS_B, T0_A, T0_B
 
 
-def _both():
+def _both(parts: bool = False):
     import olfactory_navigation_b200 as onb
     env, _ = make('T0')
     agent = onb.Agent(env, thresholds=0.5)
     mk = lambda s, t, hz: onb.SimulationHistory(s, env, agent, t, horizon=hz, reward_discount=0.99, used_gpu=False)   # noqa: E731
     ha = feed(mk, STARTS_A, np.arange(len(STARTS_A)) * 3, 1, T0_A)
     hb = feed(mk, STARTS_B, np.arange(len(STARTS_B)) + 40, 2, T0_B)
-    return ha + hb
+    return (ha + hb, ha, hb) if parts else ha + hb
+
+
+def test_history_compare_table():
+    g = golden('history_T0')
+    both, ha, hb = _both(parts=True)
+    mine = both.compare(ha, hb)
+    ref = pd.read_csv(io.StringIO(str(g['compare'][()])))
+    assert list(mine.columns) == list(ref.columns) and len(mine) == 3
+    pd.testing.assert_frame_equal(mine.astype(float), ref.astype(float), rtol=1e-12, atol=0)
 
 
 def test_history_files_match_the_reference(tmp_path):

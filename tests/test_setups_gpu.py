@@ -88,3 +88,34 @@ def test_run_test_prints_the_reference_summary(trained, capsys):
     runs = hist.runs_analysis_df
     assert np.array_equal(runs['steps_taken'], hist.steps_taken) and np.all(runs['time_s'] > 0)
     assert float(hist.general_analysis_df.loc['mean', 'delta_t1_s']) > 0
+
+
+def test_agent_in_void(trained):
+    'No odor anywhere: the single run starts from the farthest start cell and never observes anything above the threshold.'
+    import olfactory_navigation_b200 as onb
+    env, agent = trained
+    hist = onb.test_setups.test_agent_in_void(agent, horizon=40, print_progress=False, print_stats=False, print_warning=False)
+    starts = np.argwhere(env.start_probabilities > 0)
+    far = starts[int(np.argmax(env.distance_to_source(starts)))]
+    assert hist.n == 1 and np.array_equal(hist.start_points[0], far)
+    obs = np.array([o[0] for o in hist.observations])
+    assert np.all(obs[obs >= 0] == 0.0)
+    assert np.all(np.asarray(env.data) >= 0) and np.any(np.asarray(env.data) > 0)      # the agent's own environment is untouched
+
+
+def test_agents_by_environments_table(trained, tmp_path):
+    import olfactory_navigation_b200 as onb
+    env, agent = trained
+    other = onb.agents.Infotaxis_Agent(env, thresholds=agent.thresholds[1:-1].tolist())
+    untrained = onb.agents.QMDP_Agent(env, thresholds=agent.thresholds[1:-1].tolist())
+    envs = [env, env.modify(source_radius=env.source_radius + 1)]
+    table = onb.test_setups.test_agents(agent, other, untrained, environments=envs, horizon=40, print_stats=False, print_warning=False,
+                                        save_histories_path=str(tmp_path))
+    assert list(table.index.get_level_values('agent')) == ['agent_0', 'agent_0', 'agent_1', 'agent_1']      # the untrained one is skipped
+    assert table['environment'].tolist() == ['environment_0', 'environment_1'] * 2
+    plain = onb.test_setups.run_all_starts_test(agent, horizon=40, print_progress=False, print_stats=False)
+    assert np.isclose(table.loc[('agent_0', 0), 'convergence'], plain.success_count / plain.n)
+    assert np.isclose(table.loc[('agent_0', 0), 'steps_taken'], np.mean(plain.steps_taken))
+    files = sorted(os.listdir(tmp_path))
+    assert [f for f in files if f.startswith('Simualtions-')] == [f'Simualtions-agent_{a}-environment_{e}.csv' for a in (0, 1) for e in (0, 1)]
+    assert any(f.startswith('Simulation_comparison-') for f in files)
