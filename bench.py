@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--agents', type=int, default=None, help='agents per GPU (default: 100 000 for C2, 125 000 for C5)')
     ap.add_argument('--config', default='C2', choices=['C2', 'C5'],
                     help='C2 = BASELINE configs[1] (the metric\'s configuration, default); C5 = configs[4], the 2x-resolution plume of the scaling sweep (10^6 agents over 8 GPUs)')
-    ap.add_argument('--cpu-agents', type=int, default=256)
+    ap.add_argument('--cpu-agents', type=int, default=None, help='agents of the bounded CPU sample (default: 256 for C2, 64 for C5: same CPU work per sample)')
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-backup', action='store_true')
@@ -59,6 +59,8 @@ def parse():
     CONFIG = args.config
     if args.agents is None:
         args.agents = N_AGENTS if CONFIG == 'C2' else 125_000
+    if args.cpu_agents is None:
+        args.cpu_agents = 256 if CONFIG == 'C2' else 64
     return args
 
 
