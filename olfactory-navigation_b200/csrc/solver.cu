@@ -1,6 +1,8 @@
 // Environment stepping, MDP value iteration and the streaming halves of the PBVI backup.
 #include "common.cuh"
 #include "umma_gemm.cuh"
+#include <cuda_fp16.h>
+#include <cstdlib>
 
 int olf_segmax_simt(const float* b, int64_t ld, int64_t n, int K4, const float* M, int64_t ldM, int n_seg, int seg_len,
                     float* out_val, int* out_arg, cudaStream_t st);
@@ -146,6 +148,34 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_
     lo[r * ld + c] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
 }
 
+// FP16 2-way split planes with a power-of-two scale per row (umma_gemm.cu, umma_f16_kernel): one block per destination row.
+//   t = 2^(13 - floor(log2 max|v|)) so that |t v| < 2^14;  b1 = fp16(t v), b2 = fp16((t v - b1) 2^11), binv = 1 / t
+__global__ void split_planes_f16_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
+                                        __half* __restrict__ b1, __half* __restrict__ b2, float* __restrict__ binv, long long ld) {
+    __shared__ float red[8];
+    const long long r = blockIdx.y;
+    const long long dst = (long long)blockIdx.z * gridDim.y + r;
+    const float* srow = src + ((long long)blockIdx.z * rows + r) * ld_src;
+    const bool live = r < rows;
+    float mx = 0.f;
+    if (live)
+        for (int c = threadIdx.x; c < K; c += blockDim.x) mx = fmaxf(mx, fabsf(srow[c]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    const float p2 = __uint_as_float(__float_as_uint(mx) & 0x7f800000u);          // 2^floor(log2 max) (0 for zero / subnormal rows)
+    const float t = p2 > 0.f ? 8192.f / p2 : 1.f;
+    if (threadIdx.x == 0) binv[dst] = 1.f / t;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        const float y = (live && c < K) ? srow[c] * t : 0.f;
+        const __half h = __float2half_rn(y);
+        b1[dst * ld + c] = h;
+        b2[dst * ld + c] = __float2half_rn((y - __half2float(h)) * 2048.f);
+    }
+}
+
 }  // namespace
 
 // ======================================================================================================
@@ -208,6 +238,25 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
     } else {
         // split the Gamma rows into TF32 hi/lo planes with each (a,o) segment padded to a multiple of 16 rows
         const int Gs = (G + 15) & ~15;
+        const char* f16_env = getenv("OLFNAV_GEMM_F16");           // read per call: "0" selects the 3xTF32 kernel
+        if (!(f16_env && f16_env[0] == '0')) {
+            // 2-way FP16 split planes with a power-of-two scale per Gamma row (half the tensor time of 3xTF32, same accuracy)
+            const long long ldh = (m->g.Sp + 63) & ~63;
+            __half *b1 = nullptr, *b2 = nullptr;
+            float* binv = nullptr;
+            OLF_CUDA(cudaMallocAsync((void**)&b1, (size_t)nseg * Gs * ldh * sizeof(__half), st));
+            OLF_CUDA(cudaMallocAsync((void**)&b2, (size_t)nseg * Gs * ldh * sizeof(__half), st));
+            OLF_CUDA(cudaMallocAsync((void**)&binv, (size_t)nseg * Gs * sizeof(float), st));
+            dim3 grid(1, Gs, nseg);
+            split_planes_f16_kernel<<<grid, 256, 0, st>>>(gamma_ao, ld_gamma, G, m->g.Sp, b1, b2, binv, ldh);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: f16 split launch failed"); rc = OLFNAV_ERR_CUDA; }
+            if (rc == OLFNAV_OK)
+                rc = olf_umma_segmax_f16(b, ld, n, m->g.Sp, scale, b1, b2, binv, ldh, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
+            cudaFreeAsync(b1, st);
+            cudaFreeAsync(b2, st);
+            cudaFreeAsync(binv, st);
+        } else {
         const long long ldp = (m->g.Sp + 31) & ~31;
         float *hi = nullptr, *lo = nullptr;
         OLF_CUDA(cudaMallocAsync((void**)&hi, (size_t)nseg * Gs * ldp * sizeof(float), st));
@@ -222,6 +271,7 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
             rc = olf_umma_segmax(b, ld, n, m->g.Sp, hi, lo, ldp, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
         cudaFreeAsync(hi, st);
         cudaFreeAsync(lo, st);
+        }
     }
     // b . r_a : A one-row segments (exact FP32)
     if (rc == OLFNAV_OK) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, m->reward, m->g.Sp, A, 1, rew_val, rew_arg, st);

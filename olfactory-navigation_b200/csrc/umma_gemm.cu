@@ -26,6 +26,7 @@
 #include "umma_ptx.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -350,6 +351,310 @@ umma_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ============================================================================================================
+// FP16 2-way split variant (segmented max / argmax epilogue only; DESIGN §8 item 0, scripts/f16_ts_probe.cu,
+// scripts/fp16_split_study.py).  x = s a with s = 2^k per row, a1 = fp16(x), a2 = fp16((x - a1) 2^11); the B planes b1, b2 are
+// built the same way by the caller with a power-of-two scale t_j per row of B (binv[j] = 1 / t_j).
+//     a.b = (a1.b1 + 2^-11 (a1.b2 + a2.b1)) / (s t_j)
+// Three tcgen05.mma.kind::f16 per K = 16 instead of three kind::tf32 per K = 8: half the tensor time, same 2^-22 accuracy.
+// One accumulator: the cross terms of a K chunk are issued first, then the first main MMA reads the accumulator scaled by 2^-11
+// (scale-input-d), then the remaining main MMAs.  K block = 64: raw FP32 A tile of 32 KB (two TMA boxes), two FP16 B planes of
+// BN x 128 B.  A stage is released after the main pass of its chunk, so STAGES >= 2 * KCHUNK_H and TA >= KCHUNK_H.
+constexpr int BKH = 64;          // K per block in the FP16 kernel
+constexpr int A_TILE_BYTES_H = 2 * A_TILE_BYTES;
+constexpr int NTHREADS_H = 512;  // warps 0-3 TMA / MMA / TMEM alloc / idle, warps 4-11 A transform (two threads per row), warps 12-15 epilogue
+
+// KC = k-blocks per accumulator lifetime (2: 24 accumulates, as in the TF32 kernel's 4 x 32)
+template <int BN, int STAGES, int TA, int KC>
+struct SmemLayoutH {
+    static constexpr int B_TILE_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES_H + 2 * B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int A_BASE = BN <= 64 ? 128 : 256;
+    static constexpr int NUM_BARS = 3 * STAGES + 4 + TA;
+    static_assert(A_BASE + 64 * TA <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
+    static_assert(TOTAL <= 227 * 1024 && 8 * NUM_BARS + 8 <= 256, "shared memory budget");
+    static_assert(STAGES >= KC + 1 && TA >= KC, "a chunk's stages stay resident until its main pass");
+};
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A.B + D * 2^-11
+__device__ __forceinline__ void tc_mma_f16_ts_scale11(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_f16() {
+    // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// power-of-two row scale: 2^14 * 2^floor(log2 f) (f = the row's normaliser 1 / sum, so that every entry * s <= 2^14)
+__device__ __forceinline__ float row_scale_pow2(const float* a_scale, long long row, bool ok) {
+    float f = (a_scale && ok) ? a_scale[row] : 1.f;
+    if (!(f > 1e-30f && f < 1e30f)) f = 1.f;          // dead rows (sum 0: normaliser inf / nan) hold zeros; any scale will do
+    return __uint_as_float(__float_as_uint(f) & 0x7f800000u) * 16384.f;
+}
+
+template <int BN, int STAGES, int TA, int KC>
+__global__ void __launch_bounds__(NTHREADS_H, 1)
+umma_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                const __grid_constant__ CUtensorMap tmB2, const GemmParams p, const float* __restrict__ a_scale,
+                const float* __restrict__ binv) {
+    using L = SmemLayoutH<BN, STAGES, TA, KC>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+    auto a_raw = [&](int s) { return base + s * L::STAGE_BYTES; };
+    auto b_1 = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES_H; };
+    auto b_2 = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES_H + L::B_TILE_BYTES; };
+    const uint32_t bars = base + L::BAR_OFFSET;
+    auto bar_full = [&](int s) { return bars + 8 * s; };
+    auto bar_ready = [&](int s) { return bars + 8 * (STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8 * (2 * STAGES + s); };
+    auto bar_tfull = [&](int a) { return bars + 8 * (3 * STAGES + a); };
+    auto bar_tempty = [&](int a) { return bars + 8 * (3 * STAGES + 2 + a); };
+    auto bar_aempty = [&](int a) { return bars + 8 * (3 * STAGES + 4 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * L::NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t TMEM_COLS = 512;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB2) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), 8); mbar_init(bar_empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 128); }
+        for (int a = 0; a < TA; ++a) mbar_init(bar_aempty(a), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // 512 threads start with 128 registers each; the epilogue keeps BN partial sums in registers and takes what the others give up
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one_sync()) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+                int mt, nt, kbeg, kend, part;
+                unit_to_tile(p, u, mt, nt);
+                unit_k_range(p, u, kbeg, kend, part);
+                for (int kb = kbeg; kb < kend; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_full(s), A_TILE_BYTES_H + 2 * L::B_TILE_BYTES);
+                    tma_load_2d(a_raw(s), &tmA, kb * BKH, mt * BM, bar_full(s));
+                    tma_load_2d(a_raw(s) + A_TILE_BYTES, &tmA, kb * BKH + BK, mt * BM, bar_full(s));
+                    tma_load_2d(b_1(s), &tmB1, kb * BKH, nt * BN, bar_full(s));
+                    tma_load_2d(b_2(s), &tmB2, kb * BKH, nt * BN, bar_full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_f16<BN>();
+        uint32_t it = 0, ccount = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int kbeg, kend, part;
+            unit_k_range(p, u, kbeg, kend, part);
+            for (int kb0 = kbeg; kb0 < kend; kb0 += KC, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tempty(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const int nkb = min(kend - kb0, KC);
+                // cross terms a1.b2 + a2.b1 of the whole chunk
+                for (int j = 0; j < nkb; ++j) {
+                    const uint32_t itj = it + j;
+                    const int s = itj % STAGES;
+                    mbar_wait(bar_ready(s), (itj / STAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a1 = tmem_base + L::A_BASE + 64 * (itj % TA), a2 = a1 + 32;
+                        const uint64_t db1 = make_sw128_desc(b_1(s)), db2 = make_sw128_desc(b_2(s));
+#pragma unroll
+                        for (int kk = 0; kk < BKH / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);       // +32 B per K = 16 step inside the swizzle row
+                            tc_mma_f16_ts(d_tmem, a1 + kk * 8, db2 + adv, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                            tc_mma_f16_ts(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                        }
+                    }
+                    __syncwarp();
+                }
+                // main terms: D = a1.b1 + D * 2^-11 first, plain accumulation afterwards
+                for (int j = 0; j < nkb; ++j) {
+                    const uint32_t itj = it + j;
+                    const int s = itj % STAGES;
+                    if (elect_one_sync()) {
+                        const int ta = itj % TA;
+                        const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta;
+                        const uint64_t db1 = make_sw128_desc(b_1(s));
+#pragma unroll
+                        for (int kk = 0; kk < BKH / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                            if (j == 0 && kk == 0) tc_mma_f16_ts_scale11(d_tmem, a1, db1, idesc);
+                            else tc_mma_f16_ts(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                        }
+                        tc_commit(bar_empty(s));
+                        tc_commit(bar_aempty(ta));
+                        if (j == nkb - 1) tc_commit(bar_tfull(acc));
+                    }
+                    __syncwarp();
+                }
+                it += nkb;
+            }
+        }
+    }
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        // ===================== A transform: raw FP32 row (shared memory) -> a1 / a2 FP16 pairs (tensor memory) =====================
+        // thread (t, sub): row t of the tile (TMEM lane t: warps 4-7 and 8-11 both map warp % 4 to the lane quarter), 32-float half sub
+        const int t = (threadIdx.x - 128) & 127;
+        const int sub = (threadIdx.x - 128) >> 7;
+        const uint8_t* rowp = gbase + t * 128 + sub * A_TILE_BYTES;
+        const int sw = t & 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int mt, nt, kbeg, kend, part;
+            unit_to_tile(p, u, mt, nt);
+            unit_k_range(p, u, kbeg, kend, part);
+            const long long row = (long long)mt * BM + t;
+            const float sc = row_scale_pow2(a_scale, row, row < p.n_rows);
+            for (int kb = kbeg; kb < kend; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int ta = it % TA;
+                mbar_wait(bar_full(s), ph);
+                mbar_wait(bar_aempty(ta), ((it / TA) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * ta;
+                {
+                    const uint8_t* src = rowp + s * L::STAGE_BYTES;
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
+                        const float x0 = v.x * sc, x1 = v.y * sc, x2 = v.z * sc, x3 = v.w * sc;
+                        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.f, (x1 - f01.y) * 2048.f);
+                        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.f, (x3 - f23.y) * 2048.f);
+                        h[2 * c] = *reinterpret_cast<const uint32_t*>(&h01);
+                        h[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        l[2 * c] = *reinterpret_cast<const uint32_t*>(&l01);
+                        l[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    }
+                    tc_st16(th + sub * 16, h);
+                    tc_st16(th + 32 + sub * 16, l);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ready(s));
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ===================== epilogue: FP32 register accumulation + segmented max / argmax =====================
+        const int q = warp & 3;
+        const bool direct = p.ws == nullptr;
+        uint32_t ccount = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            int mt, nt;
+            unit_to_tile(p, u, mt, nt);
+            const long long row = (long long)mt * BM + q * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            const int col0 = nt * BN;
+            int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;
+            float best = -INFINITY;
+            int best_idx = 0;
+            bool dirty = false;
+            float sum[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+            int kbeg, kend, part;
+            unit_k_range(p, u, kbeg, kend, part);
+            for (int kb0 = kbeg; kb0 < kend; kb0 += KC, ++ccount) {
+                const int acc = ccount & 1;
+                const uint32_t aph = (ccount >> 1) & 1;
+                mbar_wait(bar_tfull(acc), aph);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty(acc));
+            }
+            // undo the block scales (powers of two: exact)
+            const float inv_s = 1.f / row_scale_pow2(a_scale, row, row_ok);
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] *= inv_s * ((col0 + j < p.rows_b) ? __ldg(binv + col0 + j) : 0.f);
+            if (part >= 0) {
+                float* wsrow = p.tail_ws + ((((long long)(unit_tile_index(p, u) - p.full_units) * p.tail_split + part) * BM) + q * 32 + lane) * BN;
+#pragma unroll
+                for (int j = 0; j < BN; j += 4) *reinterpret_cast<float4*>(wsrow + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+                continue;
+            }
+            auto flush = [&]() {
+                if (row_ok && cur_seg < p.n_seg) {
+                    if (direct) {
+                        p.out_val[row * p.n_seg + cur_seg] = best;
+                        p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                    } else if (dirty) {
+                        atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
+                    }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                const float x = sum[j];
+                if (r < p.seg_len && cur_seg < p.n_seg) {
+                    dirty = true;
+                    if (x > best) { best = x; best_idx = r; }
+                }
+                if (++r == p.seg_stride) {
+                    flush();
+                    r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
+                }
+            }
+            if (r != 0 && !direct) flush();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+
 // ws -> (value, first index); entries no unit touched stay (-inf, 0)
 __global__ void segmax_decode_kernel(long long n, const unsigned long long* __restrict__ ws, float* __restrict__ out_val,
                                      int* __restrict__ out_arg) {
@@ -558,4 +863,102 @@ int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K, const flo
     p.n_seg = 1; p.seg_len = rows_b; p.seg_stride = (rows_b + 15) & ~15;
     p.out_store = out; p.out_ld = out_ld;
     return umma_run(A, lda, n_rows, K, B_hi, B_lo, ldb, (rows_b + 15) & ~15, p, sm_count, st);
+}
+
+// FP16 split variant (see umma_f16_kernel): B1 / B2 are FP16 planes [rows_b x ldb] (ldb in halfs, multiple of 64, zero beyond K),
+// binv[j] = 1 / t_j the inverse power-of-two scale of row j of B, a_scale (may be NULL) the per-row normaliser of A (1 / row sum).
+int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, const float* a_scale,
+                        const void* B1, const void* B2, const float* binv, int64_t ldb, int rows_b,
+                        int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count, cudaStream_t st) {
+    OLF_REQUIRE(A && B1 && B2 && binv && out_val && out_arg, "umma_segmax_f16: null argument");
+    OLF_REQUIRE((lda % 4) == 0 && (((uintptr_t)A) & 15) == 0, "umma_segmax_f16: A must be 16-byte aligned with lda %% 4 == 0");
+    OLF_REQUIRE((ldb % 64) == 0 && ldb >= K, "umma_segmax_f16: ldb must be a multiple of 64 and >= K");
+    OLF_REQUIRE((seg_stride % 16) == 0 && seg_len <= seg_stride && rows_b == n_seg * seg_stride, "umma_segmax_f16: bad segment layout");
+    OLF_REQUIRE(n_rows > 0 && K > 0, "umma_segmax_f16: empty problem");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows_b = rows_b;
+    p.n_seg = n_seg; p.seg_len = seg_len; p.seg_stride = seg_stride;
+    p.out_val = out_val; p.out_arg = out_arg;
+    static const int wide_bn = [] { const char* e = getenv("OLFNAV_GEMM_F16_BN"); const int v = e ? atoi(e) : 128; return (v == 80 || v == 96) ? v : 128; }();
+    const int BN = rows_b <= 80 ? ((rows_b + 15) & ~15) : wide_bn;
+    p.n_rows = (int)n_rows; p.K = K;
+    p.num_m_tiles = olf_div_up(n_rows, BM);
+    p.num_n_tiles = olf_div_up(rows_b, BN);
+    p.num_k_blocks = olf_div_up(K, BKH);
+    p.num_units = p.num_m_tiles * p.num_n_tiles;
+    p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
+    const size_t n_out = (size_t)n_rows * p.n_seg;
+    if (p.num_n_tiles > 1) {
+        OLF_CUDA(cudaMallocAsync((void**)&p.ws, n_out * sizeof(unsigned long long), st));
+        OLF_CUDA(cudaMemsetAsync(p.ws, 0, n_out * sizeof(unsigned long long), st));
+    }
+    CUtensorMap tA, tB1, tB2;
+    int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    EncodeTiledFn enc = get_encode();
+    for (int k = 0; k < 2 && rc == OLFNAV_OK; ++k) {
+        cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)rows_b};
+        cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BKH, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(k ? &tB2 : &tB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(k ? B2 : B1), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { olfnav_set_error("umma_segmax_f16: cuTensorMapEncodeTiled failed (%d)", (int)r); rc = OLFNAV_ERR_CUDA; }
+    }
+    if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
+
+    int grid = p.num_units < sm_count ? p.num_units : sm_count;
+    p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
+    int tail_tiles = 0;
+    if (p.num_units > sm_count && p.num_k_blocks >= 32) {
+        const int tail = p.num_units % sm_count;
+        const int split = tail ? (sm_count / tail < 4 ? sm_count / tail : 4) : 1;
+        if (tail && split > 1) {
+            tail_tiles = tail;
+            p.full_units = p.num_units - tail;
+            p.tail_split = split;
+            p.num_units = p.full_units + tail * split;
+            OLF_CUDA(cudaMallocAsync((void**)&p.tail_ws, (size_t)tail * split * BM * BN * sizeof(float), st));
+        }
+    }
+#define OLF_LAUNCH_H(BN_, ST_, TA_, KC_)                                                                                             \
+    do {                                                                                                                         \
+        using L = SmemLayoutH<BN_, ST_, TA_, KC_>;                                                                                   \
+        static bool configured = false;                                                                                          \
+        if (!configured) {                                                                                                       \
+            OLF_CUDA(cudaFuncSetAttribute(umma_f16_kernel<BN_, ST_, TA_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); \
+            configured = true;                                                                                                   \
+        }                                                                                                                        \
+        umma_f16_kernel<BN_, ST_, TA_, KC_><<<grid, NTHREADS_H, L::TOTAL, st>>>(tA, tB1, tB2, p, a_scale, binv);                        \
+        olf_count_launch(1);                                                                                                     \
+        if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: launch failed"); rc = OLFNAV_ERR_CUDA; }     \
+    } while (0)
+    switch (BN) {
+        case 16: OLF_LAUNCH_H(16, 5, 5, 2); break;
+        case 32: OLF_LAUNCH_H(32, 5, 5, 2); break;
+        case 48: OLF_LAUNCH_H(48, 5, 5, 2); break;
+        case 64: OLF_LAUNCH_H(64, 4, 4, 2); break;
+        case 80: OLF_LAUNCH_H(80, 4, 4, 2); break;
+        case 96: OLF_LAUNCH_H(96, 4, 4, 2); break;
+        default: OLF_LAUNCH_H(128, 3, 3, 1); break;
+    }
+#undef OLF_LAUNCH_H
+    if (p.tail_ws) {
+        if (rc == OLFNAV_OK) {
+            tail_finish_kernel<<<olf_div_up((int64_t)tail_tiles * BM, 128), 128, 0, st>>>(p, BN, tail_tiles);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: tail finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        cudaFreeAsync(p.tail_ws, st);
+    }
+    if (p.ws) {
+        if (rc == OLFNAV_OK) {
+            segmax_decode_kernel<<<olf_div_up((int64_t)n_out, 256), 256, 0, st>>>((long long)n_out, p.ws, p.out_val, p.out_arg);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: decode kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        cudaFreeAsync(p.ws, st);
+    }
+    return rc;
 }

@@ -23,3 +23,10 @@ int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K,
 
 // 2-D tensor map over a row-major FP32 matrix, box = 32 floats x box_rows, 128B swizzle (K-major UMMA operand tiles).
 int olf_make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows);
+
+// Same contraction with a 2-way FP16 split (three kind::f16 MMAs per K = 16: half the tensor time of 3xTF32, same accuracy):
+//   B1 / B2 [rows_b x ldb] FP16 planes (ldb in halfs, multiple of 64, >= K, zero beyond K): b1 = fp16(t_j v), b2 = fp16((t_j v - b1) 2^11)
+//   with t_j a power of two per row; binv[j] = 1 / t_j; a_scale (may be NULL) = per-row normaliser of A (entries * a_scale <= 1).
+int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, const float* a_scale,
+                        const void* B1, const void* B2, const float* binv, int64_t ldb, int rows_b,
+                        int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count, cudaStream_t st);

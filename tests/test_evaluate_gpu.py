@@ -237,3 +237,63 @@ def test_tail_split_in_the_backup_gemm():
     assert float((g2 == g1).float().mean()) > 0.995
     same = (a2 == a1) & (g2 == g1).flatten(1).all(1)
     assert torch.equal(na2[same], na1[same])
+
+
+@pytest.mark.parametrize('B,G', [(896, 150), (300, 5), (1000, 64), (130, 33)])
+def test_backup_fp16_split_gemm_against_simt_and_tf32(B, G, monkeypatch):
+    '''
+    The backup selection's tensor path runs a 2-way FP16 split with power-of-two block scales (umma_f16_kernel, three kind::f16 MMAs
+    per K = 16, cross terms and main term in one accumulator through scale-input-d); OLFNAV_GEMM_F16=0 selects the 3xTF32 kernel.
+    Both must agree with the FP32 SIMT path: values to 1e-5 (measured: 5e-7 for FP16, 2e-6 for TF32), same choices.
+    Alpha vectors span six decades so that the per-vector scale matters.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(12)
+    bs = onb.BeliefSet(m, B)
+    for _ in range(4):
+        bs = bs.update(rng.integers(0, 4, B), np.zeros(B, dtype=int), raise_on_impossible_belief=False)
+    vals = 100 * np.abs(rng.standard_normal((G, m.padded_states))) ** 3 * 10.0 ** rng.integers(-4, 2, (G, 1))
+    alphas = torch.as_tensor(vals.astype(np.float32), device=bs._b.device)
+    H, W = m.grid_shape
+    alphas.view(G, H, -1)[:, :, W:] = 0
+    na1, a1, v1, g1 = onb.solvers.backup_device(m, bs, alphas, 0.99, 1)
+    monkeypatch.setenv('OLFNAV_GEMM_F16', '1')
+    na2, a2, v2, g2 = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    monkeypatch.setenv('OLFNAV_GEMM_F16', '0')
+    na3, a3, v3, g3 = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    for v, a, g in ((v2, a2, g2), (v3, a3, g3)):
+        np.testing.assert_allclose(v.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5)
+        assert float((a == a1).float().mean()) > 0.995 and float((g == g1).float().mean()) > 0.995
+    same = (a2 == a1) & (g2 == g1).flatten(1).all(1)
+    assert torch.equal(na2[same], na1[same])
+
+
+def test_backup_fp16_split_handles_unnormalised_and_dead_rows():
+    'Rows carried with a deferred normaliser (sum << 1) and an all-zero row: the row scale comes from the normaliser, dead rows give zeros.'
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import lib, ptr, stream, check
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(5)
+    B, G = 200, 40
+    bs = onb.BeliefSet(m, B)
+    for _ in range(3):
+        bs = bs.update(rng.integers(0, 4, B), np.zeros(B, dtype=int), raise_on_impossible_belief=False)
+    n = len(bs)
+    alphas = torch.as_tensor(np.abs(rng.standard_normal((G, m.padded_states))).astype(np.float32), device=bs._b.device)
+    H, W = m.grid_shape
+    alphas.view(G, H, -1)[:, :, W:] = 0
+    factor = torch.as_tensor(10.0 ** rng.uniform(-25, 0, n), dtype=torch.float32, device=bs._b.device)
+    raw = (bs._b[:n] * (bs._scale[:n] * factor)[:, None]).contiguous()          # rows with sums from 1e-25 to 1
+    inv = (1.0 / factor).contiguous()
+    raw[7] = 0
+    inv[7] = float('inf')
+    scaled = onb.BeliefSet(m, _buffers=(raw, inv, n), device=0)
+    _, a1, v1, g1 = onb.solvers.backup_device(m, scaled, alphas, 0.99, 1)
+    _, a2, v2, g2 = onb.solvers.backup_device(m, scaled, alphas, 0.99, 2)
+    keep = torch.ones(n, dtype=torch.bool, device=raw.device)
+    keep[7] = False
+    np.testing.assert_allclose(v2[keep].cpu().numpy(), v1[keep].cpu().numpy(), rtol=1e-5)
+    assert float((g2[keep] == g1[keep]).float().mean()) > 0.995 and float((a2[keep] == a1[keep]).float().mean()) > 0.995
