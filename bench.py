@@ -217,13 +217,17 @@ def measure_backup(onb, model, world, rank, dev, args):
     assert new_alpha.shape[0] == B
     flops = 2.0 * B * model.padded_states * ((G + 15) // 16 * 16) * model.action_count * model.observation_count
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
-    tf32_peak = peaks.get('bf16_tflops', 1590.0) / 2.0
+    f16 = os.environ.get('OLFNAV_GEMM_F16', '1') != '0'              # the backup GEMM runs the 2-way FP16 split unless switched off
+    tensor_peak = peaks.get('bf16_tflops', 1590.0) / (1.0 if f16 else 2.0)
     issued = 3.0 * flops / (ms * 1e-3) / 1e12 / world
     return {'value': B / (ms * 1e-3), 'unit': 'belief-backups/s', 'belief_points': B, 'alpha_vectors': G, 'ms_per_backup': ms, 'scaling': 'strong',
             'collective': 'all_gather of the per-belief selection ((1 + A*O) int32 per belief point: best action + alpha indices) per backup; every rank assembles all new alpha vectors from its own Gamma' if world > 1 else 'none (1 rank)',
-            'roofline': {'kernel': 'umma_ts_kernel', 'bound': 'tensor', 'achieved': issued, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': issued / tf32_peak,
-                         'note': 'issued TF32 flop (3 passes of the split-precision scheme) per GPU over the WHOLE backup time (Gamma build, GEMM, assembly, all-gather); '
-                                 'peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)'}}
+            'roofline': {'kernel': 'umma_f16_kernel' if f16 else 'umma_ts_kernel', 'bound': 'tensor', 'achieved': issued, 'peak': tensor_peak,
+                         'unit': 'TFLOP/s', 'frac': issued / tensor_peak,
+                         'note': ('issued FP16 flop (3 kind::f16 passes of the 2-way split scheme) per GPU over the WHOLE backup time (Gamma build, plane '
+                                  'split, GEMM, assembly, all-gather); peak = measured cuBLAS bf16 burst') if f16 else
+                                 ('issued TF32 flop (3 passes of the split-precision scheme) per GPU over the WHOLE backup time (Gamma build, GEMM, '
+                                  'assembly, all-gather); peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the bf16 rate)')}}
 
 
 def run_ours(args) -> None:

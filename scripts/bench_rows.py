@@ -3,7 +3,8 @@ Per-row measurements of the hot path on one B200: belief step (out
 evaluate vs G (SIMT / tcgen05), PBVI backup at C3 scale, infotaxis choice at C4 scale.  One JSON line per row.
 CUDA-event timing, >= 3 warm-ups, inputs far larger than L2.  Usage: python scripts/bench_rows.py [rows...]
 '''
-import json, os, sys, time
+import json
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import olfactory_navigation_b200 as onb
@@ -74,8 +75,10 @@ if 'backup' in rows:
         alphas = torch.as_tensor(np.abs(rng.standard_normal((G, Sp))).astype(np.float32), device=dev)
         t = timeit(lambda: onb.solvers.backup_device(m, bs, alphas, 0.99, 2), iters=3, warm=1)
         flops = 2.0 * B * S * G * m.action_count * m.observation_count
+        f16 = os.environ.get('OLFNAV_GEMM_F16', '1') != '0' and G >= 128       # solver.cu: 2-way FP16 split from G = 128 up, 3xTF32 below
         emit(row='a6 backup (gamma + select + assemble)', B=B, G=G, ms=t, belief_backups_per_s=B / t * 1e3, useful_TFLOPs=flops / t / 1e9,
-             tf32_issued_TFLOPs=3 * flops * (((G + 15) // 16 * 16) / G) / t / 1e9)
+             scheme='fp16x2 (3 kind::f16 MMAs per K=16)' if f16 else 'tf32x3 (3 kind::tf32 MMAs per K=8)',
+             issued_TFLOPs=3 * flops * (((G + 15) // 16 * 16) / G) / t / 1e9)
         del alphas
     del bs
 
