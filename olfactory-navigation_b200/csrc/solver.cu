@@ -148,34 +148,6 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_
     lo[r * ld + c] = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
 }
 
-// FP16 2-way split planes with a power-of-two scale per row (umma_gemm.cu, umma_f16_kernel): one block per destination row.
-//   t = 2^(13 - floor(log2 max|v|)) so that |t v| < 2^14;  b1 = fp16(t v), b2 = fp16((t v - b1) 2^11), binv = 1 / t
-__global__ void split_planes_f16_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
-                                        __half* __restrict__ b1, __half* __restrict__ b2, float* __restrict__ binv, long long ld) {
-    __shared__ float red[8];
-    const long long r = blockIdx.y;
-    const long long dst = (long long)blockIdx.z * gridDim.y + r;
-    const float* srow = src + ((long long)blockIdx.z * rows + r) * ld_src;
-    const bool live = r < rows;
-    float mx = 0.f;
-    if (live)
-        for (int c = threadIdx.x; c < K; c += blockDim.x) mx = fmaxf(mx, fabsf(srow[c]));
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
-    const float p2 = __uint_as_float(__float_as_uint(mx) & 0x7f800000u);          // 2^floor(log2 max) (0 for zero / subnormal rows)
-    const float t = p2 > 0.f ? 8192.f / p2 : 1.f;
-    if (threadIdx.x == 0) binv[dst] = 1.f / t;
-    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
-        const float y = (live && c < K) ? srow[c] * t : 0.f;
-        const __half h = __float2half_rn(y);
-        b1[dst * ld + c] = h;
-        b2[dst * ld + c] = __float2half_rn((y - __half2float(h)) * 2048.f);
-    }
-}
-
 }  // namespace
 
 // ======================================================================================================
@@ -248,10 +220,7 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
             OLF_CUDA(cudaMallocAsync((void**)&b1, (size_t)nseg * Gs * ldh * sizeof(__half), st));
             OLF_CUDA(cudaMallocAsync((void**)&b2, (size_t)nseg * Gs * ldh * sizeof(__half), st));
             OLF_CUDA(cudaMallocAsync((void**)&binv, (size_t)nseg * Gs * sizeof(float), st));
-            dim3 grid(1, Gs, nseg);
-            split_planes_f16_kernel<<<grid, 256, 0, st>>>(gamma_ao, ld_gamma, G, m->g.Sp, b1, b2, binv, ldh);
-            olf_count_launch(1);
-            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: f16 split launch failed"); rc = OLFNAV_ERR_CUDA; }
+            rc = olf_split_planes_f16(gamma_ao, ld_gamma, G, m->g.Sp, b1, b2, binv, ldh, Gs, nseg, st);
             if (rc == OLFNAV_OK)
                 rc = olf_umma_segmax_f16(b, ld, n, m->g.Sp, scale, b1, b2, binv, ldh, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
             cudaFreeAsync(b1, st);

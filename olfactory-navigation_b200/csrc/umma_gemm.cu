@@ -865,6 +865,48 @@ int olf_umma_store(const float* A, int64_t lda, int64_t n_rows, int K, const flo
     return umma_run(A, lda, n_rows, K, B_hi, B_lo, ldb, (rows_b + 15) & ~15, p, sm_count, st);
 }
 
+namespace {
+// FP16 2-way split planes with a power-of-two scale per row (umma_gemm.cu, umma_f16_kernel): one block per destination row.
+//   t = 2^(13 - floor(log2 max|v|)) so that |t v| < 2^14;  b1 = fp16(t v), b2 = fp16((t v - b1) 2^11), binv = 1 / t
+__global__ void split_planes_f16_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
+                                        __half* __restrict__ b1, __half* __restrict__ b2, float* __restrict__ binv, long long ld) {
+    __shared__ float red[8];
+    const long long r = blockIdx.y;
+    const long long dst = (long long)blockIdx.z * gridDim.y + r;
+    const float* srow = src + ((long long)blockIdx.z * rows + r) * ld_src;
+    const bool live = r < rows;
+    float mx = 0.f;
+    if (live)
+        for (int c = threadIdx.x; c < K; c += blockDim.x) mx = fmaxf(mx, fabsf(srow[c]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    const float p2 = __uint_as_float(__float_as_uint(mx) & 0x7f800000u);          // 2^floor(log2 max) (0 for zero / subnormal rows)
+    const float t = p2 > 0.f ? 8192.f / p2 : 1.f;
+    if (threadIdx.x == 0) binv[dst] = 1.f / t;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        const float y = (live && c < K) ? srow[c] * t : 0.f;
+        const __half h = __float2half_rn(y);
+        b1[dst * ld + c] = h;
+        b2[dst * ld + c] = __float2half_rn((y - __half2float(h)) * 2048.f);
+    }
+}
+
+}  // namespace
+
+// rows of every segment padded to rows_padded destination rows; nseg segments of `rows` source rows each
+int olf_split_planes_f16(const float* src, int64_t ld_src, int64_t rows, int K, void* b1, void* b2, float* binv, int64_t ldh,
+                         int rows_padded, int nseg, cudaStream_t st) {
+    OLF_REQUIRE(src && b1 && b2 && binv && (ldh % 64) == 0 && ldh >= K && rows_padded >= rows, "split_planes_f16: bad argument");
+    dim3 grid(1, rows_padded, nseg);
+    split_planes_f16_kernel<<<grid, 256, 0, st>>>(src, ld_src, rows, K, (__half*)b1, (__half*)b2, binv, ldh);
+    olf_count_launch(1);
+    if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("split_planes_f16: launch failed"); return OLFNAV_ERR_CUDA; }
+    return OLFNAV_OK;
+}
+
 // FP16 split variant (see umma_f16_kernel): B1 / B2 are FP16 planes [rows_b x ldb] (ldb in halfs, multiple of 64, zero beyond K),
 // binv[j] = 1 / t_j the inverse power-of-two scale of row j of B, a_scale (may be NULL) the per-row normaliser of A (1 / row sum).
 int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, const float* a_scale,

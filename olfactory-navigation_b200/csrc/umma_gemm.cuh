@@ -30,3 +30,8 @@ int olf_make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t
 int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, const float* a_scale,
                         const void* B1, const void* B2, const float* binv, int64_t ldb, int rows_b,
                         int n_seg, int seg_len, int seg_stride, float* out_val, int* out_arg, int sm_count, cudaStream_t st);
+
+// FP16 split planes of a row-major FP32 matrix (one power-of-two scale per row, see olf_umma_segmax_f16): nseg segments of `rows`
+// source rows, each padded to rows_padded destination rows; ldh in halfs (multiple of 64, >= K).
+int olf_split_planes_f16(const float* src, int64_t ld_src, int64_t rows, int K, void* b1, void* b2, float* binv, int64_t ldh,
+                         int rows_padded, int nseg, cudaStream_t st);

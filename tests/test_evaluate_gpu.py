@@ -297,3 +297,35 @@ def test_backup_fp16_split_handles_unnormalised_and_dead_rows():
     keep[7] = False
     np.testing.assert_allclose(v2[keep].cpu().numpy(), v1[keep].cpu().numpy(), rtol=1e-5)
     assert float((g2[keep] == g1[keep]).float().mean()) > 0.995 and float((a2[keep] == a1[keep]).float().mean()) > 0.995
+
+
+@pytest.mark.parametrize('G', [128, 515])
+def test_evaluate_fp16_split_gemm(G, monkeypatch):
+    '''
+    From G = 128 up evaluate_at's tensor path is the 2-way FP16 split kernel (OLFNAV_GEMM_F16=0: 3xTF32).  Both against float64 on
+    rows carried with a deferred normaliser, signed alpha vectors whose magnitudes span eight decades.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(G)
+    n = 700
+    bs = onb.BeliefSet(m, n)
+    for _ in range(5):
+        bs = bs.update(rng.integers(0, 4, n), np.zeros(n, dtype=int), raise_on_impossible_belief=False)
+    B = bs.belief_array
+    alphas = (rng.standard_normal((G, m.state_count)) * 10.0 ** rng.integers(-6, 3, (G, 1))).astype(np.float32).astype(np.float64)
+    acts = rng.integers(0, 4, G)
+    vf = onb.ValueFunction(m, alphas, acts)
+    sc = B @ alphas.T
+    norm = np.abs(B) @ np.abs(alphas).T
+    ref_g = sc.argmax(1)
+    srt = np.sort(sc, axis=1)
+    clear = srt[:, -1] - srt[:, -2] > 1e-5 * norm.max(1)
+    assert clear.mean() > 0.5
+    for flag in ('1', '0'):
+        monkeypatch.setenv('OLFNAV_GEMM_F16', flag)
+        val, arg, act = vf.evaluate_device(bs, 2)
+        err = np.abs(val.cpu().numpy() - sc.max(1)) / norm[np.arange(len(B)), ref_g]
+        assert err.max() < 1e-5, (flag, err.max())
+        assert np.array_equal(arg.cpu().numpy()[clear], ref_g[clear])
