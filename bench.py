@@ -348,7 +348,7 @@ def run_ours(args) -> None:
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'{CONFIG} run_test of a trained FSVI agent: ' + WORKLOADS[CONFIG],
-                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': 'simt-fp32' if G <= 8 else 'tcgen05-3xtf32',
+                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': 'simt-fp32' if G <= 8 else ('tcgen05-fp16x2-split' if (G >= 64 and os.environ.get('OLFNAV_GEMM_F16', '1') != '0') else 'tcgen05-3xtf32'),
                        'sharding': 'agents split across ranks, no data-path collective',
                        'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * model.padded_states * 4 / 1e9)},
             'e2e': {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},

@@ -81,7 +81,7 @@ struct olfnav_alphas {
     float* lo;           // [Gp][ld]  alpha - hi, also tf32-representable
     float* full;         // [Gp][ld]  fp32 copy (SIMT path)
     int32_t* actions;    // [G]
-    // 2-way FP16 split planes with a power-of-two scale per alpha vector (umma_f16_kernel), built when G >= 128
+    // 2-way FP16 split planes with a power-of-two scale per alpha vector (umma_f16_kernel), built when G >= 64
     void* h1;            // [Gp][ldh] fp16(t_g alpha)
     void* h2;            // [Gp][ldh] fp16((t_g alpha - h1) 2^11)
     float* binv;         // [Gp] 1 / t_g

@@ -136,8 +136,9 @@ extern "C" int olfnav_alphas_create(olfnav_alphas** out, const olfnav_model* m, 
         olfnav_alphas_destroy(a);
         return OLFNAV_ERR_CUDA;
     }
-    if (G >= 128) {
-        // FP16 split planes for the tensor path at large G (half the tensor time of 3xTF32, same accuracy)
+    if (G >= 64) {
+        // FP16 split planes for the tensor path (half the tensor time of 3xTF32, same accuracy); below G = 64 the product is HBM bound
+        // with either kernel (measured: G = 64 2.02 -> 1.97 ms, G = 75 inside the C2 step 2.17 -> 1.93 ms, G = 512 12.9 -> 8.67 ms)
         a->ldh = (m->g.Sp + 63) & ~63;
         e = cudaMalloc(&a->h1, (size_t)a->Gp * a->ldh * 2);
         if (e == cudaSuccess) e = cudaMalloc(&a->h2, (size_t)a->Gp * a->ldh * 2);

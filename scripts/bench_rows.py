@@ -63,7 +63,7 @@ if 'evaluate' in rows:
         for path in ((1, 2) if G <= 16 else (2,)):
             t = timeit(lambda: vf.evaluate_device(bs, path), iters=5 if G > 256 else 10)
             flops = 2.0 * n * S * G
-            f16 = path == 2 and G >= 128 and os.environ.get('OLFNAV_GEMM_F16', '1') != '0'     # evaluate.cu: 2-way FP16 split planes from G = 128 up
+            f16 = path == 2 and G >= 64 and os.environ.get('OLFNAV_GEMM_F16', '1') != '0'     # evaluate.cu: 2-way FP16 split planes from G = 64 up
             emit(row='a4 evaluate', G=G, path='simt' if path == 1 else ('tcgen05-fp16x2' if f16 else 'tcgen05-3xtf32'), n=n, ms=t,
                  read_GBps=4 * S * n / t / 1e6, frac_hbm=4 * S * n / t / 1e6 / HBM,
                  useful_TFLOPs=flops / t / 1e9, issued_TFLOPs=3 * 2.0 * n * Sp * (((G + 15) // 16 * 16) if G <= 128 else ((G + 127) // 128 * 128)) / t / 1e9)
