@@ -151,7 +151,8 @@ void olfnav_alphas_destroy(olfnav_alphas* a);
 /* ValueFunction.evaluate_at(BeliefSet) -> (values, actions)      agents/pbvi_agent.py:741
  * value[i] = scale[i] * max_g b[i,:].alpha_g ; arg[i] = first argmax ; action[i] = actions[arg[i]].
  * Any of value/arg/action may be NULL.  `path`: 0 = auto, 1 = FP32 SIMT kernel,
- * 2 = tcgen05 tensor-core kernel (3xTF32 split precision). */
+ * 2 = tcgen05 tensor-core kernel (split precision with FP32 accuracy: 3xTF32 below G = 64, 2-way FP16 split with power-of-two
+ *     block scales from G = 64 up; OLFNAV_GEMM_F16=0 forces 3xTF32). */
 int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a,
                     const float* b, int64_t ld, int64_t n, const float* scale,
                     float* value, int32_t* arg, int32_t* action, int path, void* stream);

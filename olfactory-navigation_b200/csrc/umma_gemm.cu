@@ -21,6 +21,10 @@
 //   warps 4-7   A transform: raw FP32 row (shared memory) -> hi / lo in tensor memory (tcgen05.st)
 //   warps 8-11  epilogue: tcgen05.ld each K-chunk's partial accumulator, FP32 register sums, segmented max/argmax
 // Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
+//
+// umma_f16_kernel (second half of this file) is the same pipeline with a 2-way FP16 split and power-of-two block scales instead of
+// 3xTF32 (three kind::f16 MMAs per K = 16, one accumulator through scale-input-d): half the tensor work per K.  It serves the backup
+// selection from G = 128 up and evaluate_at / the run_test policy from G = 64 up; OLFNAV_GEMM_F16=0 falls back to the TF32 kernel.
 #include "common.cuh"
 #include "umma_gemm.cuh"
 #include "umma_ptx.cuh"
