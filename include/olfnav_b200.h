@@ -60,8 +60,9 @@ typedef struct olfnav_env olfnav_env;          /* stepping environment on one de
 
 int         olfnav_abi_version(void);
 const char* olfnav_last_error(void);
-int         olfnav_padded_width(int W);                 /* Wp */
-int64_t     olfnav_padded_states(int H, int W);         /* Sp = H * Wp */
+int         olfnav_padded_width(int W);                 /* Wp under the default rule: W rounded up to 4, to 64 from 128 columns up */
+int         olfnav_padded_width_for(int W, int row_pad);/* Wp under an explicit rule: row_pad = 0 (by width), 4 or 64 */
+int64_t     olfnav_padded_states(int H, int W);         /* Sp = H * Wp (default rule) */
 uint64_t    olfnav_kernel_launches(void);               /* kernels this library has launched so far (process wide) */
 
 /* ------------------------------------------------------------------------------------------------
@@ -76,6 +77,10 @@ uint64_t    olfnav_kernel_launches(void);               /* kernels this library 
 int  olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O,
                          const int32_t* moves, int boundary,
                          const double* obs_table, const uint8_t* end_mask, const double* start);
+/* Same with an explicit row padding rule (see olfnav_padded_width_for); olfnav_model_create uses row_pad = 0. */
+int  olfnav_model_create_padded(olfnav_model** out, int device, int H, int W, int A, int O,
+                                const int32_t* moves, int boundary,
+                                const double* obs_table, const uint8_t* end_mask, const double* start, int row_pad);
 /* Dense stochastic-transition model — POMDP(states, actions, observations, transition_table = T[s, a, s'], observation_table,
  * end_states, start_probabilities) as built by the reference's minimal_converter
  * (agents/model_based_util/environment_converter.py:137-292, call :282-290).  Every entry point that takes an olfnav_model
@@ -117,20 +122,25 @@ int olfnav_belief_step(const olfnav_model* m,
                        uint8_t* ok,                                     /* [dev] n */
                        void* stream);
 
-/* Fused  BeliefSet.update (agents/pbvi_agent.py:783-787)  +  ValueFunction.evaluate_at of the UPDATED beliefs
- * (agents/pbvi_agent.py:741, the choose_action of the next run_test iteration, simulation.py:1454): one pass over the rows,
- * 8*S bytes of HBM traffic per agent instead of 12*S.  Same contract as olfnav_belief_step with dst_i = i (b_out != b_in)
- * followed by olfnav_evaluate(b_out, scale_out): value[i] = max_g b'_i . alpha_g (normalised), arg[i] = first argmax,
- * action[i] = alpha_actions[arg[i]]; value / arg / action may be NULL.  Needs <= 80 alpha vectors (one tensor-core tile whose partial sums fit the epilogue registers) and
- * a grid of at least two rows; returns OLFNAV_ERR_UNSUPPORTED otherwise (callers then issue the two calls). */
-int olfnav_can_fuse_policy(const olfnav_model* m, const olfnav_alphas* a);   /* 1: olfnav_belief_step_evaluate supports this pair */
+/* One-pass  BeliefSet.update (agents/pbvi_agent.py:783-787)  +  ValueFunction.evaluate_at of the UPDATED beliefs
+ * (agents/pbvi_agent.py:741, the choose_action of the next run_test iteration, simulation.py:1454): 8*S bytes of HBM traffic per
+ * agent instead of 12*S.  Same arithmetic as olfnav_belief_step followed by olfnav_evaluate(b_out, scale_out):
+ *   value[i] = max_g b'_i . alpha_g (normalised), arg[i] = first argmax, action[i] = alpha_actions[arg[i]]  (any may be NULL)
+ * but the updated rows are written GROUPED BY ACTION, 128 to a tile (the kernel's unit of work): the belief of input i lands in
+ * row row_out[i] of b_out, scale_out is indexed by that row, and b_out / scale_out must hold olfnav_fused_out_rows(m, n) rows.
+ * src_rows[i] (NULL = i) is the row of input i in b_in; b_in holds rows_in rows.  b_out != b_in.
+ * Supported when olfnav_can_fuse_policy(m, a) == 1 (<= 80 alpha vectors; grid rows padded to 64 floats; vertical moves wrap,
+ * horizontal moves clip: the BASELINE plume configurations); OLFNAV_ERR_UNSUPPORTED otherwise (callers issue the two calls). */
+int     olfnav_can_fuse_policy(const olfnav_model* m, const olfnav_alphas* a);
+int64_t olfnav_fused_out_rows(const olfnav_model* m, int64_t n);
 int olfnav_belief_step_evaluate(const olfnav_model* m, const olfnav_alphas* a,
-                                const float* b_in, float* b_out, int64_t ld, int64_t n,
+                                const float* b_in, int64_t rows_in, float* b_out, int64_t rows_out, int64_t ld, int64_t n,
                                 const int32_t* act, const int32_t* obs,  /* [dev] n */
                                 const int32_t* src_rows,                 /* [dev] n or NULL */
-                                const float* scale_in, float* scale_out, /* [dev] */
+                                const float* scale_in, float* scale_out, /* [dev] rows_in / rows_out */
                                 uint8_t* ok,                             /* [dev] n */
                                 float* value, int32_t* arg, int32_t* action, /* [dev] n or NULL */
+                                int32_t* row_out,                        /* [dev] n or NULL */
                                 void* stream);
 
 /* Belief compaction — `belief_array[~kill]`, agents/pbvi_agent.py:810-811, agents/infotaxis_agent.py:362-363.
@@ -267,8 +277,12 @@ typedef struct olfnav_sim_step_args {
     void* ev_policy_end; void* ev_update_begin; void* ev_update_end;
     /* optional: act_next != NULL (needs alphas != NULL and olfnav_can_fuse_policy(m, alphas) == 1) => the belief update of the
      * survivors also evaluates the value function on the updated rows (olfnav_belief_step_evaluate) and writes the NEXT step's
-     * action ids of the m survivors to act_next[0..m): the caller skips its own policy call for the next step */
+     * action ids of the m survivors to act_next[0..m): the caller skips its own policy call for the next step.
+     * The one-pass kernel groups the updated rows by action: brow_out[j] (j < m) receives the row of b_out that holds survivor j's
+     * belief, brow_in[i] (NULL = i) tells where agent i's belief sits in b_in, scale_in / scale_out are indexed by belief row, and
+     * both belief buffers hold belief_rows >= olfnav_fused_out_rows(m, n) rows. */
     int32_t* act_next;
+    const int32_t* brow_in; int32_t* brow_out; int64_t belief_rows;
     /* layered environments (environment.py:202-235; simulation.py:1456-1463): layer of every action id (A ints, NULL without
      * layers), thresholds laid out [L][n_thr] when thr_per_layer = 1 (agent.py:414-417), L + 1 ints of scratch for time_mode 1 */
     const int32_t* act_layer; int32_t thr_per_layer; int32_t* hist_layer;

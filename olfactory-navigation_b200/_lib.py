@@ -32,8 +32,10 @@ SIGNATURES = {
     'olfnav_last_error': (ctypes.c_char_p, []),
     'olfnav_padded_width': (_i, [_i]),
     'olfnav_padded_states': (_i64, [_i, _i]),
+    'olfnav_padded_width_for': (_i, [_i, _i]),
     'olfnav_kernel_launches': (ctypes.c_uint64, []),
     'olfnav_model_create': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    'olfnav_model_create_padded': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _i]),
     'olfnav_model_destroy': (None, [_p]),
     'olfnav_model_dims': (_i, [_p, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     'olfnav_pack_rows': (_i, [_p, _p, _p, _p, _i64, _i64, _p]),
@@ -41,8 +43,9 @@ SIGNATURES = {
     'olfnav_belief_init': (_i, [_p, _p, _i64, _i64, _p, _p]),
     'olfnav_model_create_dense': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _p, _p, _p]),
     'olfnav_belief_step': (_i, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
-    'olfnav_belief_step_evaluate': (_i, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    'olfnav_belief_step_evaluate': (_i, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     'olfnav_can_fuse_policy': (_i, [_p, _p]),
+    'olfnav_fused_out_rows': (_i64, [_p, _i64]),
     'olfnav_copy_rows': (_i, [_p, _p, _i64, _i64, _p, _p, _p, _i64, _p]),
     'olfnav_alphas_create': (_i, [ctypes.POINTER(_p), _p, _p, _i64, _p, _i, _p]),
     'olfnav_alphas_destroy': (None, [_p]),
@@ -80,6 +83,7 @@ class SimStepArgs(ctypes.Structure):
         ('counts', _p),
         ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
         ('act_next', _p),
+        ('brow_in', _p), ('brow_out', _p), ('belief_rows', _i64),
         ('act_layer', _p), ('thr_per_layer', ctypes.c_int32), ('hist_layer', _p),
     ]
 

@@ -39,17 +39,26 @@ class BeliefSimulationMixin:
         # release the buffers of a previous run BEFORE allocating the new ones: two belief buffers of a C5 shard are 2 x 61.6 GB
         # of a 180 GB part, a third one does not fit  (a `belief` taken from this agent keeps its own reference alive)
         self._bufs, self._scales = None, None
+        # run_test's one-pass update + policy kernel writes the rows grouped by action, every action's last 128-row tile padded:
+        # it asks for a few spare rows per buffer (olfnav_fused_out_rows) through _row_capacity
+        cap = max(n, 1)
+        rows = max(cap, int(getattr(self, '_row_capacity', 0) or 0))
+        b0 = torch.empty((rows, Sp), dtype=torch.float32, device=dev)
+        s0 = torch.zeros(rows, dtype=torch.float32, device=dev)
         if belief is None:
-            first = BeliefSet(model, n, device=device)
+            if n:
+                with torch.cuda.device(device):
+                    check(lib.olfnav_belief_init(model.handle(device), ptr(b0), Sp, n, ptr(s0), stream()))
         else:
             assert len(belief) == n, f'The amount of beliefs provided ({len(belief)}) to initialize the state need to match the amount of stimulations to initialize (n={n}).'
             src = belief if isinstance(belief, BeliefSet) else BeliefSet(model, belief.belief_array)
-            first = BeliefSet(model, _buffers=(src._b[:max(n, 1)].clone(), src._scale[:max(n, 1)].clone(), n), device=device)   # never clobber the caller's set
-        cap = max(n, 1)
-        if first._b.shape[0] < cap or first._b.shape[1] != Sp or not first._b.is_contiguous():
-            raise ValueError('belief set buffers have an unexpected shape')
+            if src._b.shape[1] != Sp:
+                raise ValueError('belief set buffers have an unexpected shape')
+            b0[:n].copy_(src._b[:n])                   # never clobber the caller's set
+            s0[:n].copy_(src._scale[:n])
+        first = BeliefSet(model, _buffers=(b0, s0, n), device=device)
         self._bufs = [first._b, torch.empty_like(first._b)]
-        self._scales = [first._scale, torch.empty_like(first._scale)]
+        self._scales = [first._scale, torch.zeros_like(first._scale)]
         self._cur = 0
         self._n_live = n
         self._ok = torch.empty(cap, dtype=torch.uint8, device=dev)

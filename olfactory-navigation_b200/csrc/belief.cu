@@ -539,11 +539,10 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
     if (!force_v1 && (fits256 || fits512)) {
         const int threads = (fits256 && !(force_threads == 512 && fits512)) ? 256 : 512;
         const size_t smem2 = ring_smem(threads);
-        static bool configured = false;
-        if (!configured) {
+        static OlfPerDeviceOnce configured;
+        if (configured.first()) {
             OLF_CUDA(cudaFuncSetAttribute(belief_step_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
             OLF_CUDA(cudaFuncSetAttribute(belief_step_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-            configured = true;
         }
         if (threads == 256) belief_step_tma_kernel<256><<<(unsigned)n, 256, smem2, (cudaStream_t)stream>>>(p, m->g);
         else                belief_step_tma_kernel<512><<<(unsigned)n, 512, smem2, (cudaStream_t)stream>>>(p, m->g);

@@ -40,6 +40,33 @@ void olf_count_launch(int n);
         }                                                                                      \
     } while (0)
 
+// Stream-ordered scratch that goes back to the pool on EVERY exit path (run_test catches out-of-memory and retries with more
+// batches, reference simulation.py:1346-1367: a failed attempt must not leak what it had already taken).
+struct OlfScratch {
+    cudaStream_t st;
+    void* p = nullptr;
+    explicit OlfScratch(cudaStream_t s) : st(s) {}
+    OlfScratch(const OlfScratch&) = delete;
+    OlfScratch& operator=(const OlfScratch&) = delete;
+    ~OlfScratch() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Function attributes (opt-in dynamic shared memory) belong to a device context: one flag per device, not per process.
+constexpr int OLF_MAX_DEVICES = 64;
+struct OlfPerDeviceOnce {
+    bool done[OLF_MAX_DEVICES] = {};
+    // true the first time it is asked on the current device
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= OLF_MAX_DEVICES) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // ---- grid geometry shared by every kernel ------------------------------------------------------------
 struct Geom {
     int H, W, Wp, W4;      // Wp = W rounded up to 4, W4 = Wp / 4 (float4 per grid row)
@@ -66,6 +93,9 @@ struct olfnav_model {
     float* pull_lo;
     int pull_rows, pull_rows_p;
     int64_t pull_ld;
+    // one-pass update + policy kernel (fused_step2.cu): 0 / 1 masks per action, [A][2][Sp]: coef[a][0][s'] = 1 when the cell one x-move
+    // before s' exists (its mass arrives at s'), coef[a][1][s'] = 1 when s' is the clipped edge cell of the move (it keeps its own mass)
+    float* coef;
     // dense stochastic-transition models (dense.cu; reference minimal_converter): T[s, a, s'] as [A][S][Sp] planes,
     // t_pull rows = source state s (contiguous in s'), t_push rows = destination state s' (contiguous in s)
     int dense;
@@ -86,6 +116,7 @@ struct olfnav_alphas {
     void* h2;            // [Gp][ldh] fp16((t_g alpha - h1) 2^11)
     float* binv;         // [Gp] 1 / t_g
     int64_t ldh;         // row stride (halfs), multiple of 64
+    int f16_eval;        // evaluate_at takes the FP16 split kernel (G >= 64; below that both kernels are HBM bound)
 };
 
 struct olfnav_env {
@@ -147,10 +178,12 @@ int olf_belief_step_launch(const olfnav_model* m, const float* b_in, float* b_ou
 // evaluate with caller-provided scratch (val, idx: n entries each); any of value / arg / action may be NULL
 int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float* b, int64_t ld, int64_t n, const float* scale,
                       float* val, int* idx, float* value, int32_t* arg, int32_t* action, int path, cudaStream_t st);
-// fused belief update + evaluation (fused_step.cu); n = upper bound of the rows, n_dev (optional) = exact device-side count
-int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const float* b_in, float* b_out, int64_t ld, int64_t n,
-                          const int32_t* act, const int32_t* obs, const int32_t* src_rows, const float* scale_in, float* scale_out,
-                          uint8_t* ok, float* value, int32_t* arg, int32_t* action, const int* n_dev, cudaStream_t st);
+// one-pass belief update + evaluation (fused_step2.cu); n = upper bound of the rows, n_dev (optional) = exact device-side count;
+// src_rows[i] = agent slot of input i (NULL = i), in_rows[slot] = its row in b_in (NULL = slot)
+int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const float* b_in, int64_t rows_in, float* b_out, int64_t rows_out,
+                          int64_t ld, int64_t n, const int32_t* act, const int32_t* obs, const int32_t* src_rows, const int32_t* in_rows,
+                          const float* scale_in, float* scale_out, uint8_t* ok, float* value, int32_t* arg, int32_t* action,
+                          int32_t* row_out, const int* n_dev, cudaStream_t st);
 // dense-model kernels (dense.cu)
 int olf_dense_belief_step(const olfnav_model* m, const float* b_in, float* b_out, int64_t ld, int64_t n, const int32_t* act,
                           const int32_t* obs, const int32_t* src_rows, const int32_t* dst_rows, const float* scale_in,

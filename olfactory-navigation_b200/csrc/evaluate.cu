@@ -136,7 +136,9 @@ extern "C" int olfnav_alphas_create(olfnav_alphas** out, const olfnav_model* m, 
         olfnav_alphas_destroy(a);
         return OLFNAV_ERR_CUDA;
     }
-    if (G >= 64) {
+    a->f16_eval = G >= 64 ? 1 : 0;
+    {
+        // FP16 split planes (always built: the one-pass update + policy kernel uses them at every G; evaluate_at from G = 64 up)
         // FP16 split planes for the tensor path (half the tensor time of 3xTF32, same accuracy); below G = 64 the product is HBM bound
         // with either kernel (measured: G = 64 2.02 -> 1.97 ms, G = 75 inside the C2 step 2.17 -> 1.93 ms, G = 512 12.9 -> 8.67 ms)
         a->ldh = (m->g.Sp + 63) & ~63;
@@ -169,7 +171,7 @@ int olf_evaluate_into(const olfnav_model* m, const olfnav_alphas* a, const float
     if (path == 1) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, a->full, a->ld, 1, a->G, val, idx, st);
     else {
         const char* f16_env = getenv("OLFNAV_GEMM_F16");           // read per call: "0" selects the 3xTF32 kernel
-        if (a->h1 && !(f16_env && f16_env[0] == '0'))
+        if (a->h1 && a->f16_eval && !(f16_env && f16_env[0] == '0'))
             rc = olf_umma_segmax_f16(b, ld, n, m->g.Sp, scale, a->h1, a->h2, a->binv, a->ldh, a->Gp, 1, a->G, a->Gp, val, idx, m->sm_count, st);
         else
             rc = olf_umma_segmax(b, ld, n, m->g.Sp, a->hi, a->lo, a->ld, a->Gp, 1, a->G, a->Gp, val, idx, m->sm_count, st);
@@ -188,12 +190,8 @@ extern "C" int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a, co
     if (n == 0) return OLFNAV_OK;
     OLF_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    float* val = nullptr;
-    int* idx = nullptr;
-    OLF_CUDA(cudaMallocAsync((void**)&val, (size_t)n * sizeof(float), st));
-    OLF_CUDA(cudaMallocAsync((void**)&idx, (size_t)n * sizeof(int), st));
-    const int rc = olf_evaluate_into(m, a, b, ld, n, scale, val, idx, value, arg, action, path, st);
-    cudaFreeAsync(val, st);
-    cudaFreeAsync(idx, st);
-    return rc;
+    OlfScratch val(st), idx(st);
+    OLF_CUDA(val.alloc((size_t)n * sizeof(float)));
+    OLF_CUDA(idx.alloc((size_t)n * sizeof(int)));
+    return olf_evaluate_into(m, a, b, ld, n, scale, val.as<float>(), idx.as<int>(), value, arg, action, path, st);
 }

@@ -174,16 +174,16 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
     if (m->dense) return olf_dense_infotaxis(m, b, ld, n, scale, action, dH, st);
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_INFOTAXIS_V1"); return e && e[0] == '1'; }();
     if (!force_v1 && m->pull_rows <= 128) {
-        float* sums = nullptr;
         const int ld_sums = m->pull_rows;
-        OLF_CUDA(cudaMallocAsync((void**)&sums, (size_t)n * ld_sums * sizeof(float), st));
+        OlfScratch s_sums(st);
+        OLF_CUDA(s_sums.alloc((size_t)n * ld_sums * sizeof(float)));
+        float* sums = s_sums.as<float>();
         int rc = olf_umma_store(b, ld, n, m->g.Sp, m->pull_hi, m->pull_lo, m->pull_ld, m->pull_rows, sums, ld_sums, m->sm_count, st);
         if (rc == OLFNAV_OK) {
             infotaxis_finish_kernel<<<olf_div_up(n, IF_WARPS), IF_WARPS * 32, 0, st>>>(m->g, (int)n, b, ld, scale, sums, ld_sums, action, dH);
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("infotaxis_choose: finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
-        cudaFreeAsync(sums, st);
         return rc;
     }
     if (m->g.O > IT_MAXO) {

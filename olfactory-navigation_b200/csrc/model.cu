@@ -24,8 +24,17 @@ void olfnav_set_error(const char* fmt, ...) {
 
 extern "C" const char* olfnav_last_error(void) { return g_err; }
 extern "C" int olfnav_abi_version(void) { return OLFNAV_ABI_VERSION; }
-extern "C" int olfnav_padded_width(int W) { return (W + 3) & ~3; }
-extern "C" int64_t olfnav_padded_states(int H, int W) { return (int64_t)H * ((W + 3) & ~3); }
+// Row padding of the belief layout.  Narrow grids: Wp = W rounded up to 4 (rows start 16-byte aligned).  Grids of 128 columns and
+// more: Wp = W rounded up to 64 floats, so that a grid row is a whole number of 128-byte cache lines (a vertical move shifts a
+// belief by whole lines: measured on B200, 256-byte row segments written at a 16-byte offset stream at 4.8 TB/s, line-aligned ones at
+// 5.9 TB/s, scripts/write_pattern_bench.cu) and the state space a whole number of 64-state K blocks of the tcgen05 kernels
+// (C2: 371 -> 384 columns, +3.2 % bytes).  row_pad = 0 picks by width; 4 / 64 force a rule (OLFNAV_ROW_PAD in the Python layer).
+extern "C" int olfnav_padded_width_for(int W, int row_pad) {
+    const int pad = row_pad > 0 ? row_pad : (W >= 128 ? 64 : 4);
+    return (W + pad - 1) / pad * pad;
+}
+extern "C" int olfnav_padded_width(int W) { return olfnav_padded_width_for(W, 0); }
+extern "C" int64_t olfnav_padded_states(int H, int W) { return (int64_t)H * olfnav_padded_width(W); }
 
 static int set_boundary(int boundary, int* wrap_y, int* wrap_x) {
     switch (boundary) {
@@ -44,9 +53,15 @@ static inline int bmove(int v, int d, int n, int wrap) {
     return v;
 }
 
-extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O,
-                                   const int32_t* moves, int boundary,
+extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W, int A, int O, const int32_t* moves, int boundary,
                                    const double* obs_table, const uint8_t* end_mask, const double* start) {
+    return olfnav_model_create_padded(out, device, H, W, A, O, moves, boundary, obs_table, end_mask, start, 0);
+}
+
+extern "C" int olfnav_model_create_padded(olfnav_model** out, int device, int H, int W, int A, int O,
+                                          const int32_t* moves, int boundary,
+                                          const double* obs_table, const uint8_t* end_mask, const double* start, int row_pad) {
+    OLF_REQUIRE(row_pad == 0 || row_pad == 4 || row_pad == 64, "model_create: row_pad must be 0 (by width), 4 or 64");
     OLF_REQUIRE(out && moves && obs_table && end_mask && start, "model_create: null argument");
     OLF_REQUIRE(H >= 1 && W >= 1 && (int64_t)H * W < (1LL << 30), "model_create: bad grid %d x %d", H, W);
     OLF_REQUIRE(A >= 1 && A <= OLFNAV_MAX_ACTIONS, "model_create: A must be in [1,%d]", OLFNAV_MAX_ACTIONS);
@@ -78,7 +93,7 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
     memset(m, 0, sizeof(*m));
     m->device = device;
     Geom& g = m->g;
-    g.H = H; g.W = W; g.Wp = (W + 3) & ~3; g.W4 = g.Wp / 4; g.S = H * W; g.Sp = H * g.Wp;
+    g.H = H; g.W = W; g.Wp = olfnav_padded_width_for(W, row_pad); g.W4 = g.Wp / 4; g.S = H * W; g.Sp = H * g.Wp;
     g.A = A; g.O = O; g.wrap_y = wy; g.wrap_x = wx;
     g.div_w4 = (g.W4 > 1) ? (unsigned)(((1ULL << 32) + g.W4 - 1) / g.W4) : 0u;
     for (int a = 0; a < A; ++a) { g.moves[a][0] = moves[2 * a]; g.moves[a][1] = moves[2 * a + 1]; }
@@ -138,6 +153,19 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
             }
     }
 
+    // x-move masks of the one-pass update + policy kernel (see olfnav_model::coef)
+    std::vector<float> h_coef((size_t)A * 2 * Sp, 0.f);
+    for (int a = 0; a < A; ++a) {
+        const int dx = g.moves[a][1];
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int sp = y * g.Wp + x;
+                const int xs = x - dx;                                        // source column of the move
+                h_coef[((size_t)a * 2 + 0) * Sp + sp] = (wx || (xs >= 0 && xs < W)) ? 1.f : 0.f;
+                h_coef[((size_t)a * 2 + 1) * Sp + sp] = (!wx && dx != 0 && bmove(x, dx, W, 0) == x) ? 1.f : 0.f;
+            }
+    }
+
     cudaError_t e = cudaSuccess;
     auto up = [&](void** dptr, const void* src, size_t bytes) {
         if (e != cudaSuccess) return;
@@ -151,6 +179,7 @@ extern "C" int olfnav_model_create(olfnav_model** out, int device, int H, int W,
     up((void**)&m->end_mask, h_end.data(), h_end.size());
     up((void**)&m->pull_hi, h_phi.data(), h_phi.size() * sizeof(float));
     up((void**)&m->pull_lo, h_plo.data(), h_plo.size() * sizeof(float));
+    up((void**)&m->coef, h_coef.data(), h_coef.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
         olfnav_set_error("model_create: %s", cudaGetErrorString(e));
@@ -165,7 +194,7 @@ extern "C" void olfnav_model_destroy(olfnav_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
-    cudaFree(m->pull_hi); cudaFree(m->pull_lo); cudaFree(m->t_pull); cudaFree(m->t_push);
+    cudaFree(m->pull_hi); cudaFree(m->pull_lo); cudaFree(m->coef); cudaFree(m->t_pull); cudaFree(m->t_push);
     delete m;
 }
 

@@ -273,10 +273,11 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
 
     // 4. fused belief update of the survivors into rows 0..m-1 of the other buffer (grid = n, exact count on the device)
     if (a->ev_update_begin) OLF_CUDA(cudaEventRecord((cudaEvent_t)a->ev_update_begin, st));
-    if (a->act_next && alphas)       // ... fused with the evaluation of the updated rows = the next step's policy
-        rc = olf_fused_step_launch(m, alphas, a->b_in, a->b_out, a->ld, n, a->act_c, a->obs_c, a->src_rows, a->scale_in, a->scale_out,
-                                   a->ok, nullptr, nullptr, a->act_next, a->counts, st);
-    else
+    if (a->act_next && alphas) {     // ... fused with the evaluation of the updated rows = the next step's policy
+        OLF_REQUIRE(a->brow_out && a->belief_rows >= olfnav_fused_out_rows(m, n), "sim_step: the one-pass update needs brow_out and belief_rows >= olfnav_fused_out_rows");
+        rc = olf_fused_step_launch(m, alphas, a->b_in, a->belief_rows, a->b_out, a->belief_rows, a->ld, n, a->act_c, a->obs_c, a->src_rows, a->brow_in,
+                                   a->scale_in, a->scale_out, a->ok, nullptr, nullptr, a->act_next, a->brow_out, a->counts, st);
+    } else
         rc = olf_belief_step_launch(m, a->b_in, a->b_out, a->ld, n, a->act_c, a->obs_c, a->src_rows, nullptr, a->scale_in, a->scale_out,
                                     a->ok, a->counts, stream);
     if (rc != OLFNAV_OK) return rc;

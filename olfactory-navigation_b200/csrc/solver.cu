@@ -199,11 +199,13 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
     const int A = m->g.A, O = m->g.O, nseg = A * O;
     if (path == 0) path = ((long long)G * nseg <= 64) ? 1 : 2;
 
-    float *seg_val = nullptr, *rew_val = nullptr;
-    int* rew_arg = nullptr;
-    OLF_CUDA(cudaMallocAsync((void**)&seg_val, (size_t)n * nseg * sizeof(float), st));
-    OLF_CUDA(cudaMallocAsync((void**)&rew_val, (size_t)n * A * sizeof(float), st));
-    OLF_CUDA(cudaMallocAsync((void**)&rew_arg, (size_t)n * A * sizeof(int), st));
+    // scratch is returned to the pool on every exit path, the failing ones included (OlfScratch)
+    OlfScratch s_seg(st), s_rew(st), s_arg(st), s_p1(st), s_p2(st), s_inv(st);
+    OLF_CUDA(s_seg.alloc((size_t)n * nseg * sizeof(float)));
+    OLF_CUDA(s_rew.alloc((size_t)n * A * sizeof(float)));
+    OLF_CUDA(s_arg.alloc((size_t)n * A * sizeof(int)));
+    float *seg_val = s_seg.as<float>(), *rew_val = s_rew.as<float>();
+    int* rew_arg = s_arg.as<int>();
     int rc = OLFNAV_OK;
     if (path == 1) {
         rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, gamma_ao, ld_gamma, nseg, G, seg_val, best_g, st);
@@ -215,22 +217,19 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
         if (!(f16_env && f16_env[0] == '0') && (G >= 128 || (f16_env && f16_env[0] == '1'))) {
             // 2-way FP16 split planes with a power-of-two scale per Gamma row (half the tensor time of 3xTF32, same accuracy)
             const long long ldh = (m->g.Sp + 63) & ~63;
-            __half *b1 = nullptr, *b2 = nullptr;
-            float* binv = nullptr;
-            OLF_CUDA(cudaMallocAsync((void**)&b1, (size_t)nseg * Gs * ldh * sizeof(__half), st));
-            OLF_CUDA(cudaMallocAsync((void**)&b2, (size_t)nseg * Gs * ldh * sizeof(__half), st));
-            OLF_CUDA(cudaMallocAsync((void**)&binv, (size_t)nseg * Gs * sizeof(float), st));
+            OLF_CUDA(s_p1.alloc((size_t)nseg * Gs * ldh * sizeof(__half)));
+            OLF_CUDA(s_p2.alloc((size_t)nseg * Gs * ldh * sizeof(__half)));
+            OLF_CUDA(s_inv.alloc((size_t)nseg * Gs * sizeof(float)));
+            __half *b1 = s_p1.as<__half>(), *b2 = s_p2.as<__half>();
+            float* binv = s_inv.as<float>();
             rc = olf_split_planes_f16(gamma_ao, ld_gamma, G, m->g.Sp, b1, b2, binv, ldh, Gs, nseg, st);
             if (rc == OLFNAV_OK)
                 rc = olf_umma_segmax_f16(b, ld, n, m->g.Sp, scale, b1, b2, binv, ldh, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
-            cudaFreeAsync(b1, st);
-            cudaFreeAsync(b2, st);
-            cudaFreeAsync(binv, st);
         } else {
         const long long ldp = (m->g.Sp + 31) & ~31;
-        float *hi = nullptr, *lo = nullptr;
-        OLF_CUDA(cudaMallocAsync((void**)&hi, (size_t)nseg * Gs * ldp * sizeof(float), st));
-        OLF_CUDA(cudaMallocAsync((void**)&lo, (size_t)nseg * Gs * ldp * sizeof(float), st));
+        OLF_CUDA(s_p1.alloc((size_t)nseg * Gs * ldp * sizeof(float)));
+        OLF_CUDA(s_p2.alloc((size_t)nseg * Gs * ldp * sizeof(float)));
+        float *hi = s_p1.as<float>(), *lo = s_p2.as<float>();
         {
             dim3 grid(olf_div_up(ldp, 256), Gs, nseg);           // one launch for all (a, o) segments
             split_planes_kernel<<<grid, 256, 0, st>>>(gamma_ao, ld_gamma, G, m->g.Sp, hi, lo, ldp);
@@ -239,8 +238,6 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
         }
         if (rc == OLFNAV_OK)
             rc = olf_umma_segmax(b, ld, n, m->g.Sp, hi, lo, ldp, nseg * Gs, nseg, G, Gs, seg_val, best_g, m->sm_count, st);
-        cudaFreeAsync(hi, st);
-        cudaFreeAsync(lo, st);
         }
     }
     // b . r_a : A one-row segments (exact FP32)
@@ -250,9 +247,6 @@ extern "C" int olfnav_backup_select(const olfnav_model* m, const float* b, int64
         olf_count_launch(1);
         if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("backup_select: pick launch failed"); rc = OLFNAV_ERR_CUDA; }
     }
-    cudaFreeAsync(seg_val, st);
-    cudaFreeAsync(rew_val, st);
-    cudaFreeAsync(rew_arg, st);
     return rc;
 }
 

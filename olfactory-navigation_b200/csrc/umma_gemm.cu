@@ -382,22 +382,6 @@ struct SmemLayoutH {
     static_assert(STAGES >= KC + 1 && TA >= KC, "a chunk's stages stay resident until its main pass");
 };
 
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// D = A.B + D * 2^-11
-__device__ __forceinline__ void tc_mma_f16_ts_scale11(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
-}
-template <int BN>
-__host__ __device__ constexpr uint32_t make_idesc_f16() {
-    // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
-    return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 // power-of-two row scale: 2^14 * 2^floor(log2 f) (f = the row's normaliser 1 / sum, so that every entry * s <= 2^14)
 __device__ __forceinline__ float row_scale_pow2(const float* a_scale, long long row, bool ok) {
     float f = (a_scale && ok) ? a_scale[row] : 1.f;
@@ -744,11 +728,9 @@ int make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t out
 template <int BN, int STAGES, int TA>
 int launch_ts(const CUtensorMap& tA, const CUtensorMap& tBh, const CUtensorMap& tBl, const GemmParams& p, int grid, cudaStream_t st) {
     using L = SmemLayoutTS<BN, STAGES, TA>;
-    static bool configured = false;
-    if (!configured) {
+    static OlfPerDeviceOnce configured;
+    if (configured.first())
         OLF_CUDA(cudaFuncSetAttribute(umma_ts_kernel<BN, STAGES, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
     umma_ts_kernel<BN, STAGES, TA><<<grid, NTHREADS, L::TOTAL, st>>>(tA, tBh, tBl, p);
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
@@ -773,8 +755,10 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
     p.ws = nullptr;
     const size_t n_out = (size_t)n_rows * p.n_seg;
+    OlfScratch ws(st), tail_ws(st);
     if (!p.out_store && p.num_n_tiles > 1) {
-        OLF_CUDA(cudaMallocAsync((void**)&p.ws, n_out * sizeof(unsigned long long), st));
+        OLF_CUDA(ws.alloc(n_out * sizeof(unsigned long long)));
+        p.ws = ws.as<unsigned long long>();
         OLF_CUDA(cudaMemsetAsync(p.ws, 0, n_out * sizeof(unsigned long long), st));
     }
 
@@ -789,7 +773,7 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
     int rc = make_map_2d(&tA, A, (uint64_t)K, (uint64_t)n_rows, (uint64_t)lda * 4, BM, a_promo);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBh, B_hi, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
     if (rc == OLFNAV_OK) rc = make_map_2d(&tBl, B_lo, (uint64_t)ldb, (uint64_t)rows_b_stored, (uint64_t)ldb * 4, BN);
-    if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
+    if (rc != OLFNAV_OK) return rc;
 
     int grid = p.num_units < sm_count ? p.num_units : sm_count;
     // tail split: more than one wave of units and a last wave that is at most half full
@@ -804,7 +788,8 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
             p.full_units = p.num_units - tail;
             p.tail_split = split;
             p.num_units = p.full_units + tail * split;
-            OLF_CUDA(cudaMallocAsync((void**)&p.tail_ws, (size_t)tail * split * BM * BN * sizeof(float), st));
+            OLF_CUDA(tail_ws.alloc((size_t)tail * split * BM * BN * sizeof(float)));
+            p.tail_ws = tail_ws.as<float>();
         }
     }
     // A in tensor memory: shared-memory stage = 16 KB raw A + 2 B planes of BN x 128 B (as many as fit ~216 KB);
@@ -825,7 +810,6 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma: tail finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
-        cudaFreeAsync(p.tail_ws, st);
     }
     if (p.ws) {
         if (rc == OLFNAV_OK) {
@@ -833,7 +817,6 @@ static int umma_run(const float* A, int64_t lda, int64_t n_rows, int K, const fl
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax: decode kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
-        cudaFreeAsync(p.ws, st);
     }
     return rc;
 }
@@ -935,8 +918,10 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     p.num_units = p.num_m_tiles * p.num_n_tiles;
     p.group_w = p.num_n_tiles < 4 ? p.num_n_tiles : 4;
     const size_t n_out = (size_t)n_rows * p.n_seg;
+    OlfScratch ws(st), tail_ws(st);
     if (p.num_n_tiles > 1) {
-        OLF_CUDA(cudaMallocAsync((void**)&p.ws, n_out * sizeof(unsigned long long), st));
+        OLF_CUDA(ws.alloc(n_out * sizeof(unsigned long long)));
+        p.ws = ws.as<unsigned long long>();
         OLF_CUDA(cudaMemsetAsync(p.ws, 0, n_out * sizeof(unsigned long long), st));
     }
     CUtensorMap tA, tB1, tB2;
@@ -952,7 +937,7 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { olfnav_set_error("umma_segmax_f16: cuTensorMapEncodeTiled failed (%d)", (int)r); rc = OLFNAV_ERR_CUDA; }
     }
-    if (rc != OLFNAV_OK) { if (p.ws) cudaFreeAsync(p.ws, st); return rc; }
+    if (rc != OLFNAV_OK) return rc;
 
     int grid = p.num_units < sm_count ? p.num_units : sm_count;
     p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
@@ -965,16 +950,17 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
             p.full_units = p.num_units - tail;
             p.tail_split = split;
             p.num_units = p.full_units + tail * split;
-            OLF_CUDA(cudaMallocAsync((void**)&p.tail_ws, (size_t)tail * split * BM * BN * sizeof(float), st));
+            OLF_CUDA(tail_ws.alloc((size_t)tail * split * BM * BN * sizeof(float)));
+            p.tail_ws = tail_ws.as<float>();
         }
     }
 #define OLF_LAUNCH_H(BN_, ST_, TA_, KC_)                                                                                             \
     do {                                                                                                                         \
         using L = SmemLayoutH<BN_, ST_, TA_, KC_>;                                                                                   \
-        static bool configured = false;                                                                                          \
-        if (!configured) {                                                                                                       \
-            OLF_CUDA(cudaFuncSetAttribute(umma_f16_kernel<BN_, ST_, TA_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL)); \
-            configured = true;                                                                                                   \
+        static OlfPerDeviceOnce configured;                                                                                      \
+        if (configured.first() &&                                                                                                \
+            cudaFuncSetAttribute(umma_f16_kernel<BN_, ST_, TA_, KC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) { \
+            olfnav_set_error("umma_segmax_f16: cudaFuncSetAttribute failed"); rc = OLFNAV_ERR_CUDA; break;                       \
         }                                                                                                                        \
         umma_f16_kernel<BN_, ST_, TA_, KC_><<<grid, NTHREADS_H, L::TOTAL, st>>>(tA, tB1, tB2, p, a_scale, binv);                        \
         olf_count_launch(1);                                                                                                     \
@@ -996,7 +982,6 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: tail finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
-        cudaFreeAsync(p.tail_ws, st);
     }
     if (p.ws) {
         if (rc == OLFNAV_OK) {
@@ -1004,7 +989,6 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: decode kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
-        cudaFreeAsync(p.ws, st);
     }
     return rc;
 }

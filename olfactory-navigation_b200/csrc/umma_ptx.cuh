@@ -102,4 +102,22 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = A.B + D * 2^-11
+__device__ __forceinline__ void tc_mma_f16_ts_scale11(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
+// kind::f16 instruction descriptor
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_f16() {
+    // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
 }  // namespace

@@ -110,6 +110,9 @@ class POMDP:
             moves, boundary = _infer_grid(R[:, :, 0], H, W)
         self.moves = np.ascontiguousarray(moves, dtype=np.int32).reshape(A, 2)
         self.boundary = boundary
+        # row padding rule of the device layout (olfnav_padded_width_for): 0 = by width (64 floats from 128 columns up, else 4);
+        # OLFNAV_ROW_PAD=4|64 forces one for the models built while it is set
+        self.row_pad = int(os.environ.get('OLFNAV_ROW_PAD', '0') or 0)
         expected = _move_table(H, W, self.moves, boundary)
         if not np.array_equal(expected, R[:, :, 0]):
             raise NotImplementedError('reachable_states_table is not a unit-step grid move table')
@@ -136,8 +139,13 @@ class POMDP:
         return self.state_grid.shape
 
     @property
+    def padded_width(self) -> int:
+        H, W = self.grid_shape
+        return int(lib.olfnav_padded_width_for(W, 0 if self.dense else getattr(self, 'row_pad', 0))) if not self.dense else (W + 3) // 4 * 4
+
+    @property
     def padded_states(self) -> int:
-        return int(lib.olfnav_padded_states(*self.grid_shape))
+        return self.grid_shape[0] * self.padded_width
 
     def handle(self, device: int = None):
         device = current_device() if device is None else device
@@ -151,9 +159,9 @@ class POMDP:
                                                     ptr(self.start_probabilities)))
                 self._handles[device] = _Handle(h, lib.olfnav_model_destroy)
                 return self._handles[device].h
-            check(lib.olfnav_model_create(ctypes.byref(h), device, H, W, self.action_count, self.observation_count,
-                                          ptr(self.moves), _lib.BOUNDARY[self.boundary], ptr(self.observation_table),
-                                          ptr(end), ptr(self.start_probabilities)))
+            check(lib.olfnav_model_create_padded(ctypes.byref(h), device, H, W, self.action_count, self.observation_count,
+                                                 ptr(self.moves), _lib.BOUNDARY[self.boundary], ptr(self.observation_table),
+                                                 ptr(end), ptr(self.start_probabilities), getattr(self, 'row_pad', 0)))
             self._handles[device] = _Handle(h, lib.olfnav_model_destroy)
         return self._handles[device].h
 
@@ -347,6 +355,8 @@ class BeliefSet:
         '''
         BeliefSet.update followed by ValueFunction.evaluate_at of the updated set (agents/pbvi_agent.py:783-787 then :741) as
         ONE device pass (olfnav_belief_step_evaluate).  Every row is kept (failed rows: ok False, scale 0).
+        The kernel writes the updated rows grouped by action; this convenience wrapper gathers them back into input order
+        (run_test keeps them where they are and carries the row map instead).
         Returns (new BeliefSet, ok bool tensor, values f32, alpha index i32, action i32) — device tensors.
         '''
         dev = self._b.device
@@ -355,17 +365,33 @@ class BeliefSet:
         n = int(act.shape[0])
         rows = None if src_rows is None else torch.as_tensor(np.asarray(src_rows), dtype=torch.int32, device=dev).contiguous()
         assert obs.shape == (n,) and (rows is not None or n == self._n)
-        out_b = torch.empty((max(n, 1), self._b.shape[1]), dtype=torch.float32, device=dev)
-        out_s = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        h = self.model.handle(self.device)
+        if lib.olfnav_can_fuse_policy(h, value_function.handle(self.device)) != 1:
+            # outside what the one-pass kernel covers (more than 80 alpha vectors, clipped vertical / wrapped horizontal moves,
+            # narrow unpadded grids, dense models): the two calls it stands for
+            out_b = torch.empty((max(n, 1), self._b.shape[1]), dtype=torch.float32, device=dev)
+            out_s = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+            ok = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(self.device):
+                check(lib.olfnav_belief_step(h, ptr(self._b), ptr(out_b), self.ld, n, ptr(act), ptr(obs), ptr(rows), None, ptr(self._scale),
+                                             ptr(out_s), ptr(ok), stream()))
+            new = BeliefSet(self.model, _buffers=(out_b, out_s, n), device=self.device)
+            val, arg, action = value_function.evaluate_device(new)
+            return new, ok[:n].bool(), val, arg, action
+        cap = max(int(lib.olfnav_fused_out_rows(h, n)), 1)
+        out_b = torch.empty((cap, self._b.shape[1]), dtype=torch.float32, device=dev)
+        out_s = torch.zeros(cap, dtype=torch.float32, device=dev)
         ok = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
         val = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
         arg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         action = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        row_out = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(self.device):
-            check(lib.olfnav_belief_step_evaluate(self.model.handle(self.device), value_function.handle(self.device), ptr(self._b), ptr(out_b),
+            check(lib.olfnav_belief_step_evaluate(h, value_function.handle(self.device), ptr(self._b), self._b.shape[0], ptr(out_b), cap,
                                                   self.ld, n, ptr(act), ptr(obs), ptr(rows), ptr(self._scale), ptr(out_s), ptr(ok),
-                                                  ptr(val), ptr(arg), ptr(action), stream()))
-        new = BeliefSet(self.model, _buffers=(out_b, out_s, n), device=self.device)
+                                                  ptr(val), ptr(arg), ptr(action), ptr(row_out), stream()))
+        idx = row_out[:n].long()
+        new = BeliefSet(self.model, _buffers=(out_b[idx].contiguous() if n else out_b[:1], out_s[idx].contiguous() if n else out_s[:1], n), device=self.device)
         return new, ok[:n].bool(), val[:n], arg[:n], action[:n]
 
     def union(self, other: 'BeliefSet') -> 'BeliefSet':

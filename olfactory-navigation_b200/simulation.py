@@ -574,7 +574,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     from .agents.pbvi_agent import BeliefSimulationMixin
     from .pomdp import current_device
     import ctypes
-    if not isinstance(agent, BeliefSimulationMixin):
+    # The device environment step bins the odor cue only: a space-aware agent (observation id = odor bin x position cell,
+    # reference agent.py:422-434) goes through the reference's host-side protocol loop instead.
+    if not isinstance(agent, BeliefSimulationMixin) or getattr(agent, 'space_aware', False):
         return _run_generic(agent, n, start_points, time_shift, environment, time_loop, horizon, initialization_values,
                             reward_discount, distance_metric, print_progress)
     device = current_device()
@@ -583,12 +585,22 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
 
-    agent.initialize_state(n, **initialization_values)
     model = agent.model
     model_h = model.handle(device)
     vf = getattr(agent, 'value_function', None)
     is_infotaxis = not hasattr(agent, 'value_function')
     alphas_h = None if is_infotaxis else vf.handle(device)
+    # One-pass step: the belief update of a step also evaluates the value function on the updated rows and delivers the next
+    # step's actions (olfnav_belief_step_evaluate: 8 S instead of 12 S bytes per agent-step).  The kernel keeps the rows grouped by
+    # action, so the loop carries a row map (brow) next to the beliefs and asks the agent for a few spare rows per buffer.
+    # OLFNAV_FUSED_STEP=0 keeps the two kernels (belief step, then evaluate).
+    fused = (not is_infotaxis and os.environ.get('OLFNAV_FUSED_STEP', '1') != '0'
+             and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
+    agent._row_capacity = int(lib.olfnav_fused_out_rows(model_h, n)) if fused else 0
+    try:
+        agent.initialize_state(n, **initialization_values)
+    finally:
+        agent._row_capacity = 0
     hist = SimulationHistory(start_points=start_points, environment=environment, agent=agent, time_shift=time_shift,
                              horizon=horizon, reward_discount=reward_discount, distance_metric=distance_metric, used_gpu=True)
 
@@ -656,10 +668,16 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                                           int(getattr(agent, 'gemm_path', 0)), stream()))
 
     args = SimStepArgs()
-    # OLFNAV_FUSED_STEP=1: the belief update of a step also evaluates the value function on the updated rows (one pass over the
-    # beliefs, olfnav_belief_step_evaluate) and delivers the next step's actions.  Opt-in: bit-identical rows, not yet faster (r1).
-    fused = (not is_infotaxis and os.environ.get('OLFNAV_FUSED_STEP', '0') == '1'
-             and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
+    brow = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
+    brow_valid = False                 # False: agent i's belief is row i (start of the run, or after an explicit compaction)
+
+    def rows_to_slot_order(m: int) -> None:
+        'Gather the m live belief rows back into agent order (row i = agent i): before a compaction by mask and at the end of the run.'
+        src, dst = agent._cur, 1 - agent._cur
+        with torch.cuda.device(device):
+            check(lib.olfnav_copy_rows(ptr(agent._bufs[src]), ptr(agent._bufs[dst]), agent._bufs[src].stride(0), model.padded_states,
+                                       ptr(brow[cur]), ptr(agent._scales[src]), ptr(agent._scales[dst]), m, stream()))
+        agent._cur = dst
     n_live, cur = n, 0
     have_act = False                   # the next step's actions were computed ahead of time (see the end of the loop body)
     iterator = range(horizon)
@@ -695,8 +713,13 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
         args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
         args.counts = counts.data_ptr()
-        args.act_next = recs[(i + 1) & 1]['act'].data_ptr() if (fused and i + 1 < horizon) else None
-        if fused and i + 1 < horizon and rec_free[(i + 1) & 1] is not None:
+        # (also on the last step of the horizon: the policy rides along for free and the rows stay grouped until the end of the run)
+        args.act_next = recs[(i + 1) & 1]['act'].data_ptr() if fused else None
+        if fused:
+            args.brow_in = brow[cur].data_ptr() if brow_valid else None
+            args.brow_out = brow[1 - cur].data_ptr()
+            args.belief_rows = int(b_cur.shape[0])
+        if fused and rec_free[(i + 1) & 1] is not None:
             main.wait_event(rec_free[(i + 1) & 1])             # the next record set receives its actions during this step
         if timing is not None:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -747,8 +770,12 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             timing.append((n_live, evs, m))
         agent._cur, agent._n_live, agent._action_ids, agent._dropped = 1 - agent._cur, m, None, None
         cur = 1 - cur
+        brow_valid = fused
         if n_fail or n_end:
             # rare: some survivors must still go (impossible update / end of the recording): explicit compaction
+            if fused and brow_valid and m:
+                rows_to_slot_order(m)
+                brow_valid = False
             keep = ~term_c[:m].bool()
             rows = torch.nonzero(keep).flatten()
             k = int(rows.numel())
@@ -767,6 +794,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     flush(0)
     if n_live == 0:
         agent._bufs = None
+    elif fused and brow_valid:
+        rows_to_slot_order(n_live)         # the agent's state is left in agent order, like after the two-kernel loop
     return hist
 
 
@@ -800,7 +829,9 @@ def _run_generic(agent, n, start_points, time_shift, environment, time_loop, hor
             ok = np.ones(len(reached), dtype=bool)
         at_end = (ts + i + 1) >= (math.inf if time_loop else environment.timesteps)
         term = reached | at_end | ~np.asarray(ok, dtype=bool)
-        hist.add_step(actions=action, next_positions=pos, observations=observation, reached_source=reached, interupt=term)
+        # the history records the odor cue only (reference simulation.py:1489), not the position columns of a space-aware observation
+        hist.add_step(actions=action, next_positions=pos, observations=(observation[:, 0] if agent.space_aware else observation),
+                      reached_source=reached, interupt=term)
         pos, ts = pos[~term], ts[~term]
         agent.kill(simulations_to_kill=term)
         if len(pos) == 0:

@@ -32,8 +32,10 @@ def test_library_exports_every_declared_symbol():
 def test_no_compute_free_entry_points():
     from olfactory_navigation_b200 import _lib
     assert _lib.lib.olfnav_abi_version() == 1
-    assert _lib.lib.olfnav_padded_width(371) == 372
-    assert _lib.lib.olfnav_padded_states(83, 371) == 83 * 372
+    assert _lib.lib.olfnav_padded_width(371) == 384
+    assert _lib.lib.olfnav_padded_states(83, 371) == 83 * 384          # wide grids: rows padded to 64 floats (whole cache lines)
+    assert _lib.lib.olfnav_padded_width_for(371, 4) == 372 and _lib.lib.olfnav_padded_width_for(21, 64) == 64
+    assert _lib.lib.olfnav_padded_width(50) == 52
 
 
 def test_product_never_imports_the_oracle():

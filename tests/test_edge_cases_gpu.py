@@ -139,7 +139,7 @@ def test_argument_errors_are_status_codes():
         check(lib.olfnav_belief_step(h, b.data_ptr() + 4, ptr(b), Sp, 1, ptr(i32), ptr(i32), None, None, ptr(s), ptr(s), ptr(u8), stream()))
     vf = onb.ValueFunction(m, np.ones((3, m.state_count)), np.arange(3))
     with pytest.raises(OlfnavError):          # the fused kernel cannot run in place
-        check(lib.olfnav_belief_step_evaluate(h, vf.handle(0), ptr(b), ptr(b), Sp, 2, ptr(i32), ptr(i32), None, ptr(s), ptr(s), ptr(u8), None, None, None, stream()))
+        check(lib.olfnav_belief_step_evaluate(h, vf.handle(0), ptr(b), 2, ptr(b), 2, Sp, 2, ptr(i32), ptr(i32), None, ptr(s), ptr(s), ptr(u8), None, None, None, None, stream()))
     torch.cuda.synchronize()                   # the context is still healthy
     assert bool((onb.BeliefSet(m, 2)._b >= 0).all())
 

@@ -1,9 +1,12 @@
 '''
-Fused belief update + value-function evaluation (olfnav_belief_step_evaluate) against the two separate C-ABI calls it
-replaces (olfnav_belief_step then olfnav_evaluate) and against the oracle.
+One-pass belief update + value-function evaluation (olfnav_belief_step_evaluate, csrc/fused_step2.cu) against the two separate
+C-ABI calls it replaces (olfnav_belief_step then olfnav_evaluate) and against the oracle.
 Bar: updated rows BIT-EXACT with olfnav_belief_step (same arithmetic, same operation order); `ok` flags exact; normalisers
 within 1e-6 relative (different summation order); values within 1e-5 relative; argmax / action indices exact wherever the
 float64 margin between the two best candidates exceeds 1e-5 relative (documented ties below that).
+The kernel covers models whose grid rows are padded to 64 floats (every grid of >= 128 columns; OLFNAV_ROW_PAD=64 forces it on the
+tiny test grids), vertical moves that wrap and horizontal moves that clip — the BASELINE plume configurations; everything else takes
+the two calls (BeliefSet.update_and_evaluate does that by itself, the raw entry point answers OLFNAV_ERR_UNSUPPORTED).
 '''
 import numpy as np
 import pytest
@@ -12,6 +15,55 @@ import torch
 from conftest import ALL_CFGS, make, oracle_model
 
 pytestmark = pytest.mark.gpu
+
+_FUSABLE = {}
+
+
+def fusable(name):
+    '''
+    Fresh agents on models the one-pass kernel covers:
+      T1p   the T1 golden geometry (15 x 21, wrap_vertical) with rows padded to 64 floats
+      wide  9 x 150 wrap_vertical (padded to 192 by the default rule), thresholds [0.3, 0.6] (O = 4)
+      diag  12 x 40 wrap_vertical padded to 64, all nine unit moves (diagonals and "stay")
+      C2    the BASELINE shape
+    '''
+    if name in _FUSABLE:
+        return _FUSABLE[name]
+    import os
+    import olfactory_navigation_b200 as onb
+    old = os.environ.get('OLFNAV_ROW_PAD')
+    try:
+        if name in ('T1p', 'diag'):
+            os.environ['OLFNAV_ROW_PAD'] = '64'
+        if name == 'T1p':
+            c = onb.synthetic.config('T1')
+            agent = onb.agents.QMDP_Agent(onb.Environment(**c['env_kwargs']), thresholds=c['thresholds'])
+        elif name == 'wide':
+            rng = np.random.default_rng(5)
+            data = rng.random((8, 5, 140)) * (rng.random((8, 5, 140)) < 0.4)
+            env = onb.Environment(data, [2, 0], source_radius=1.0, margins=[2, 5], boundary_condition='wrap_vertical')
+            agent = onb.agents.PBVI_Agent(env, thresholds=[0.3, 0.6])
+        elif name == 'diag':
+            rng = np.random.default_rng(6)
+            data = rng.random((4, 12, 40)) * (rng.random((4, 12, 40)) < 0.5)
+            env = onb.Environment(data, [6, 0], source_radius=0.5, margins=0, boundary_condition='wrap_vertical')
+            moves = np.array([[dy, dx] for dy in (-1, 0, 1) for dx in (-1, 0, 1)])
+            agent = onb.agents.PBVI_Agent(env, thresholds=[0.3, 0.6], actions=moves)
+        else:
+            _, agent = make('C2')
+    finally:
+        if old is None:
+            os.environ.pop('OLFNAV_ROW_PAD', None)
+        else:
+            os.environ['OLFNAV_ROW_PAD'] = old
+    assert agent.model.padded_width % 64 == 0
+    _FUSABLE[name] = agent
+    return agent
+
+
+def _is_fused(m, vf):
+    from olfactory_navigation_b200._lib import lib
+    return lib.olfnav_can_fuse_policy(m.handle(0), vf.handle(0)) == 1
 
 
 def _random_inputs(m, n, G, seed, point_masses=True):
@@ -58,16 +110,18 @@ def _compare(new, ok, val, arg, action, ref, vf_actions):
     return rows, good
 
 
-@pytest.mark.parametrize('cfg', ALL_CFGS)
+@pytest.mark.parametrize('cfg', ['T1p', 'wide', 'diag', 'C2'] + ALL_CFGS)
 @pytest.mark.parametrize('G', [3, 20, 75, 80])
 def test_fused_matches_separate_calls(cfg, G):
     import olfactory_navigation_b200 as onb
-    _, agent = make(cfg)
+    one_pass = cfg in ('T1p', 'wide', 'diag', 'C2')
+    agent = fusable(cfg) if one_pass else make(cfg)[1]
     m = agent.model
     n = 300
     B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=G)
     act[5], obs[6] = 99, -3                                           # invalid ids fail the row
     vf = onb.ValueFunction(m, alphas, alpha_actions)
+    assert _is_fused(m, vf) == one_pass
     bs = onb.BeliefSet(m, B)
     ref = _separate(onb, m, vf, bs, act, obs)
     new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
@@ -81,13 +135,13 @@ def test_fused_matches_separate_calls(cfg, G):
     assert clear.mean() > 0.9
 
 
-@pytest.mark.parametrize('cfg', ['T0', 'T1', 'T2', 'T3'])
+@pytest.mark.parametrize('cfg', ['T1p', 'wide', 'diag', 'T0', 'T2'])
 def test_fused_against_oracle(cfg):
     import olfactory_navigation_b200 as onb
     from oracle import refloader
     refloader.install_oracle_toolkit()
     import pomdp_toolkit as tk
-    _, agent = make(cfg)
+    agent = fusable(cfg) if cfg in ('T1p', 'wide', 'diag') else make(cfg)[1]
     m, om = agent.model, oracle_model(agent.model)
     n, G = 200, 9
     B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=11)
@@ -103,11 +157,11 @@ def test_fused_against_oracle(cfg):
     assert np.array_equal(action.cpu().numpy()[okn][clear], np.asarray(ra)[clear])
 
 
-@pytest.mark.parametrize('cfg', ['T0', 'T1', 'T3'])
+@pytest.mark.parametrize('cfg', ['T1p', 'wide', 'T0'])
 def test_fused_compacting_row_list(cfg):
     'src_rows: row i of the output is the update of source row src_rows[i] (the survivors of a simulation step).'
     import olfactory_navigation_b200 as onb
-    _, agent = make(cfg)
+    agent = fusable(cfg) if cfg in ('T1p', 'wide') else make(cfg)[1]
     m = agent.model
     n, G = 260, 17
     B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=5)
@@ -130,6 +184,7 @@ def test_fused_full_size():
     alphas = np.abs(rng.standard_normal((G, m.state_count))).astype(np.float32).astype(np.float64)
     alpha_actions = rng.integers(0, 4, G)
     vf = onb.ValueFunction(m, alphas, alpha_actions)
+    assert _is_fused(m, vf)
     bs = onb.BeliefSet(m, n)
     for step in range(3):
         act = rng.integers(0, 4, n)
@@ -146,11 +201,62 @@ def test_fused_full_size():
         bs = new
 
 
-def test_unsupported_falls_out_loudly():
+def test_stream_k_split_many_tiles():
+    '''
+    20 000 agents on the wide grid = 160 tiles on 148 SMs: every CTA owns a fraction of a tile more than one tile, so most tiles are
+    cut into two segments whose partial sums and normaliser shares are added by the finishing kernel.  Uniform and skewed action
+    mixes (one action with a single agent, one without any).
+    '''
     import olfactory_navigation_b200 as onb
-    from olfactory_navigation_b200._lib import OlfnavError
-    _, agent = make('T0')
+    agent = fusable('wide')
+    m = agent.model
+    rng = np.random.default_rng(9)
+    n, G = 20000, 33
+    alphas = np.abs(rng.standard_normal((G, m.state_count))).astype(np.float32).astype(np.float64)
+    alpha_actions = rng.integers(0, 4, G)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    bs = onb.BeliefSet(m, n)
+    for _ in range(2):
+        bs = bs.update(rng.integers(0, 4, n), np.zeros(n, dtype=int))
+    for mix in ('uniform', 'skewed'):
+        act = rng.integers(0, 4, n) if mix == 'uniform' else np.where(rng.random(n) < 0.7, 1, 3)
+        if mix == 'skewed':
+            act[1234] = 0
+        obs = (rng.random(n) < 0.1).astype(int)
+        ref = _separate(onb, m, vf, bs, act, obs)
+        new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
+        _compare(new, ok, val, arg, action, ref, alpha_actions)
+        good = ok.cpu().numpy()
+        np.testing.assert_allclose(val.cpu().numpy()[good], ref[2].cpu().numpy()[good], rtol=1e-5)
+        assert (arg.cpu().numpy()[good] == ref[3].cpu().numpy()[good]).mean() > 0.995
+
+
+def test_unsupported_models_take_the_two_calls():
+    'The raw entry point answers UNSUPPORTED outside its coverage; BeliefSet.update_and_evaluate issues the two calls instead.'
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200._lib import lib, ptr, stream, OK, ERR_UNSUPPORTED
+    _, agent = make('T0')                                              # 'stop' boundary, rows padded to 4
+    m = agent.model
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, 10, 9, seed=1)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    assert not _is_fused(m, vf)
+    bs = onb.BeliefSet(m, B)
+    dev = bs._b.device
+    cap = int(lib.olfnav_fused_out_rows(m.handle(0), 10))
+    out_b, out_s = torch.zeros((cap, bs._b.shape[1]), device=dev), torch.zeros(cap, device=dev)
+    i32 = torch.zeros(10, dtype=torch.int32, device=dev)
+    u8 = torch.zeros(10, dtype=torch.uint8, device=dev)
+    rc = lib.olfnav_belief_step_evaluate(m.handle(0), vf.handle(0), ptr(bs._b), 10, ptr(out_b), cap, bs.ld, 10, ptr(i32), ptr(i32), None,
+                                         ptr(bs._scale), ptr(out_s), ptr(u8), None, None, None, None, stream())
+    assert rc == ERR_UNSUPPORTED
+    new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
+    assert len(new) == 10
+    # more than 80 alpha vectors on a model the kernel covers otherwise
+    agent = fusable('T1p')
     m = agent.model
     B, act, obs, alphas, alpha_actions = _random_inputs(m, 10, 81, seed=1)
-    with pytest.raises(OlfnavError):
-        onb.BeliefSet(m, B).update_and_evaluate(onb.ValueFunction(m, alphas, alpha_actions), act, obs)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    assert not _is_fused(m, vf)
+    new, ok, val, arg, action = onb.BeliefSet(m, B).update_and_evaluate(vf, act, obs)
+    sc = new.belief_array[ok.cpu().numpy()] @ alphas.T
+    np.testing.assert_allclose(val.cpu().numpy()[ok.cpu().numpy()], sc.max(1), rtol=1e-5)

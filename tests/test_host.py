@@ -145,3 +145,42 @@ def test_base_agent_persistence(tmp_path):
     moved = ag.modify_environment(env2)
     assert type(moved) is type(ag) and moved.environment is env2 and np.array_equal(moved.thresholds, ag.thresholds)
     assert ag.size_on_memory() > ag.model.observation_table.nbytes
+
+
+def test_generic_loop_records_the_odor_cue_of_space_aware_agents():
+    '''
+    Host-driven protocol loop with a SPACE-AWARE custom agent: the agent receives the (n, 1 + dims) observation, the history records
+    the odor cue only (reference simulation.py:1489: `observation[:,0] if agent.space_aware else observation`).
+    '''
+    import olfactory_navigation_b200 as onb
+    from olfactory_navigation_b200 import simulation
+    env, _ = make('T1')
+
+    class Wanderer(onb.Agent):
+        def initialize_state(self, n=1):
+            self.n_alive, self.seen = n, []
+
+        def choose_action(self):
+            return self.action_set[self.rng.integers(0, len(self.action_set), self.n_alive)]
+
+        def update_state(self, action, observation, source_reached):
+            assert observation.shape == (self.n_alive, 1 + self.environment.dimensions)
+            self.seen.append(observation.copy())
+            return None
+
+        def kill(self, simulations_to_kill):
+            self.n_alive -= int(np.sum(simulations_to_kill))
+
+    agent = Wanderer(env, thresholds=0.5, space_aware=True, rng=2)
+    n, horizon = 12, 25
+    starts = env.random_start_points(n, np.random.default_rng(0))
+    hist = simulation._run_generic(agent, n, starts, np.zeros(n, dtype=int), environment=env, time_loop=True, horizon=horizon,
+                                   initialization_values={}, reward_discount=0.99, distance_metric='l1', print_progress=False)
+    obs = hist.observations                    # used to raise: (n, 3) rows written into an (n,) record
+    assert len(obs) == len(hist) and obs[0].shape == (n,)
+    live = np.arange(n)
+    for step, seen in enumerate(agent.seen):
+        assert np.array_equal(obs[step][live], seen[:, 0])
+        assert np.array_equal(hist.positions[step][live], seen[:, 1:].astype(int))
+        live = live[hist.done_at_step[live] != step + 1]
+    assert len(hist.simulation_dfs) == n
