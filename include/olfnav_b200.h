@@ -173,6 +173,9 @@ int olfnav_evaluate(const olfnav_model* m, const olfnav_alphas* a,
  * ---------------------------------------------------------------------------------------------- */
 int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
                             int32_t* action, float* dH, void* stream);
+/* Agents of the last olfnav_infotaxis_choose call on this model whose best two actions were closer than the FP32 error bound and
+ * were therefore re-evaluated in float64 (host int; synchronises `stream`). */
+int olfnav_infotaxis_last_unsure(const olfnav_model* m, int32_t* count, void* stream);
 
 /* BeliefSet.entropies   agents/infotaxis_agent.py:257 : H[i] = -sum b log b of the normalised row */
 int olfnav_entropies(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,

@@ -83,6 +83,8 @@ struct olfnav_model {
     Geom g;
     float* obs;        // [A_eff][O][Sp]   P(o | arrive s'), zero in padding columns
     float* obs_ent;    // [A_eff][Sp]      C(s') = sum_o O_o(s') log O_o(s')   (infotaxis)
+    double* obs_ent64; // the same in double (float64 re-evaluation of near-tied infotaxis choices)
+    int* it_unsure;    // [1] agents re-evaluated by the last infotaxis_choose call
     float* reward;     // [A][Sp]          r_a(s) = 1[R_a(s) in end states]
     float* start;      // [Sp]
     uint8_t* end_mask; // [Sp]

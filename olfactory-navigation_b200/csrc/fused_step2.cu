@@ -25,12 +25,14 @@
 // A operand is chosen per (row, K block) from the block's maximum (the normaliser of the row is not known before its last block)
 // and undone when the block's partial sum is added to the FP32 register sums — block floating point with FP32 accumulation.
 //
-// Warp groups (640 threads, one CTA per SM):
-//   WG0  warps 0-3    gather producers: one elected lane each, 32 rows of the tile (16 gather4 per K block)
+// Warp groups (512 threads, one CTA per SM; setmaxnreg moves registers from WG0 to the others — the pool is what the CTA was
+// launched with, 512 x 128):
+//   WG0  warp 0  producer: rows 0-63 of the tile (TMA gather4) + the table slices of the block
+//        warp 1  producer: the alpha planes of the block + rows 64-127 of the tile
+//        warp 2  TMEM allocation, MMA issuer          warp 3  store issuer
 //   WG1  warps 4-7    update + A transform of the even K blocks (thread = row = TMEM lane)
 //   WG2  warps 8-11   ... of the odd K blocks
 //   WG3  warps 12-15  epilogue: tcgen05.ld of each block's accumulator, FP32 register sums, partial sums out per segment
-//   WG4  warp 16 MMA issuer, warp 17 store issuer, warp 18 alpha-plane / table loader, warp 19 TMEM allocation
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -46,7 +48,7 @@ namespace {
 constexpr int F2_BK = 64;                  // states per K block
 constexpr int F2_STAGES = 4;
 constexpr int F2_TA = 4;                   // TMEM slots of the A operand
-constexpr int F2_THREADS = 640;
+constexpr int F2_THREADS = 512;
 constexpr int F2_BOX = BM * 128;           // bytes of one 32-float box of 128 rows
 constexpr int F2_A_BYTES = 2 * F2_BOX;     // raw / updated tile of a K block: 128 rows x 64 floats
 constexpr int F2_MAX_O = 6;                // likelihood slices staged per K block
@@ -125,7 +127,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + L::OFF_BARS;
-    auto bar_fullA = [&](int s) { return bars + 8 * s; };                       // gathered rows + table slices landed (4 producers + loader)
+    auto bar_fullA = [&](int s) { return bars + 8 * s; };                       // gathered rows + table slices landed (2 producers)
     auto bar_fullB = [&](int s) { return bars + 8 * (F2_STAGES + s); };         // alpha planes landed
     auto bar_ready = [&](int s) { return bars + 8 * (2 * F2_STAGES + s); };     // row updated in place, A operand in tensor memory
     auto bar_emptyA = [&](int s) { return bars + 8 * (3 * F2_STAGES + s); };    // the stores of the tile have read it
@@ -139,22 +141,22 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 512;
 
-    if (warp == 16 && lane == 0) {
+    if (warp == 3 && lane == 0) {
         for (int s = 0; s < F2_STAGES; ++s) {
-            mbar_init(bar_fullA(s), 5); mbar_init(bar_fullB(s), 1); mbar_init(bar_ready(s), 4);
+            mbar_init(bar_fullA(s), 2); mbar_init(bar_fullB(s), 1); mbar_init(bar_ready(s), 4);
             mbar_init(bar_emptyA(s), 1); mbar_init(bar_emptyB(s), 1);
         }
         for (int t = 0; t < F2_TA; ++t) mbar_init(bar_aempty(t), 1);
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 17 && lane == 0) {
+    if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmIn) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmOut) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB1) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB2) : "memory");
     }
-    if (warp == 19) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -166,45 +168,121 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     const int KB = p.KB;
 
     if (warp < 4) {
-        // ===================== gather producers =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // 32 row indices of the tile stay in registers over the K loop
-        uint32_t it = 0;
-        for (long long g = R.g0; g < R.g1;) {
-            const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-            const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
-            const int a = p.tile_act[tile];
-            const int shift = p.dy[a] * p.Wp;                       // source frame = output frame - dy grid rows (wrap_y: modulo Sp)
-            const int* sl = p.slot_src + (long long)tile * BM + warp * 32;
-            int r4[8][4];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { const int r = sl[4 * q + e]; r4[q][e] = r < 0 ? 0 : r; }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp < 2) {
+            // ===================== producers: gathered rows (64 each), table slices (warp 0), alpha planes (warp 1) =====================
             if (elect_one_sync()) {
-                for (int j = 0; j < nblk; ++j, ++it) {
-                    const int s = it % F2_STAGES;
-                    const uint32_t ph = (it / F2_STAGES) & 1;
-                    int c = (kb0 + j) * F2_BK - shift;
-                    if (c < 0) c += p.Sp;
-                    if (c >= p.Sp) c -= p.Sp;
-                    mbar_wait(bar_emptyA(s), ph ^ 1);
-                    mbar_expect_tx(bar_fullA(s), F2_A_BYTES / 4);
-                    const uint32_t dst = base + s * L::STAGE + warp * 32 * 128;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        f2_gather4(dst + q * 512, &tmIn, c, r4[q][0], r4[q][1], r4[q][2], r4[q][3], bar_fullA(s));
-                        f2_gather4(dst + F2_BOX + q * 512, &tmIn, c + 32, r4[q][0], r4[q][1], r4[q][2], r4[q][3], bar_fullA(s));
+                uint32_t it = 0;
+                for (long long g = R.g0; g < R.g1;) {
+                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
+                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+                    const int a = p.tile_act[tile];
+                    const int shift = p.dy[a] * p.Wp;                   // source frame = output frame - dy grid rows (wrap_y: modulo Sp)
+                    const bool coef = p.dx[a] != 0;
+                    const int4* sl = reinterpret_cast<const int4*>(p.slot_src + (long long)tile * BM + warp * 64);
+                    const float* obs_a = p.obs_tab + (size_t)((p.obs_per_action ? a : 0) * p.O) * p.Sp;
+                    const float* coef_a = p.coef + (size_t)a * 2 * p.Sp;
+                    for (int j = 0; j < nblk; ++j, ++it) {
+                        const int s = it % F2_STAGES;
+                        const uint32_t ph = (it / F2_STAGES) & 1;
+                        const int k0 = (kb0 + j) * F2_BK;
+                        int c = k0 - shift;
+                        if (c < 0) c += p.Sp;
+                        if (c >= p.Sp) c -= p.Sp;
+                        const uint32_t st = base + s * L::STAGE;
+                        if (warp == 1) {
+                            mbar_wait(bar_emptyB(s), ph ^ 1);
+                            mbar_expect_tx(bar_fullB(s), 2 * L::B_TILE);
+                            tma_load_2d(st + L::OFF_B1, &tmB1, k0, 0, bar_fullB(s));
+                            tma_load_2d(st + L::OFF_B2, &tmB2, k0, 0, bar_fullB(s));
+                        }
+                        mbar_wait(bar_emptyA(s), ph ^ 1);
+                        mbar_expect_tx(bar_fullA(s), F2_A_BYTES / 2 + (warp == 0 ? (uint32_t)(p.O + (coef ? 2 : 0)) * F2_BK * 4 : 0u));
+                        const uint32_t dst = st + warp * 64 * 128;
+#pragma unroll 4
+                        for (int q = 0; q < 16; ++q) {
+                            int4 r = __ldg(sl + q);                       // rows of 4 consecutive slots (-1: empty slot, any valid row will do)
+                            r.x = max(r.x, 0); r.y = max(r.y, 0); r.z = max(r.z, 0); r.w = max(r.w, 0);
+                            f2_gather4(dst + q * 512, &tmIn, c, r.x, r.y, r.z, r.w, bar_fullA(s));
+                            f2_gather4(dst + F2_BOX + q * 512, &tmIn, c + 32, r.x, r.y, r.z, r.w, bar_fullA(s));
+                        }
+                        if (warp == 0) {
+                            for (int o = 0; o < p.O; ++o)
+                                f2_bulk_1d(st + L::OFF_TAB + o * F2_BK * 4, obs_a + (size_t)o * p.Sp + k0, F2_BK * 4, bar_fullA(s));
+                            if (coef) {
+                                f2_bulk_1d(st + L::OFF_TAB + F2_MAX_O * F2_BK * 4, coef_a + k0, F2_BK * 4, bar_fullA(s));
+                                f2_bulk_1d(st + L::OFF_TAB + (F2_MAX_O + 1) * F2_BK * 4, coef_a + p.Sp + k0, F2_BK * 4, bar_fullA(s));
+                            }
+                        }
                     }
+                    g += nblk;
                 }
-            } else {
-                it += nblk;
             }
-            __syncwarp();
-            g += nblk;
+        } else if (warp == 2) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = make_idesc_f16<BN>();
+            const uint32_t total = (uint32_t)(R.g1 - R.g0);
+            for (uint32_t it = 0; it < total; ++it) {
+                const int s = it % F2_STAGES;
+                const uint32_t ph = (it / F2_STAGES) & 1;
+                const int acc = it & 1;
+                mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+                mbar_wait(bar_ready(s), ph);
+                mbar_wait(bar_fullB(s), ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const int ta = it % F2_TA;
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta, a2 = a1 + 32;
+                    const uint64_t db1 = make_sw128_desc(base + s * L::STAGE + L::OFF_B1), db2 = make_sw128_desc(base + s * L::STAGE + L::OFF_B2);
+                    // cross terms a1.b2 + a2.b1 first, then D = a1.b1 + D * 2^-11 and the remaining main terms
+#pragma unroll
+                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                        tc_mma_f16_ts(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
+                        tc_mma_f16_ts(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                        if (kk == 0) tc_mma_f16_ts_scale11(d_tmem, a1, db1, idesc);
+                        else tc_mma_f16_ts(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                    }
+                    tc_commit(bar_emptyB(s));
+                    tc_commit(bar_aempty(ta));
+                    tc_commit(bar_tfull(acc));
+                }
+                __syncwarp();
+            }
+        } else {
+            // ===================== store issuer: updated tile -> 128 consecutive rows of b_out =====================
+            if (elect_one_sync()) {
+                uint32_t it = 0;
+                for (long long g = R.g0; g < R.g1;) {
+                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
+                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+                    for (int j = 0; j < nblk; ++j, ++it) {
+                        const int s = it % F2_STAGES;
+                        mbar_wait(bar_ready(s), (it / F2_STAGES) & 1);
+                        const uint32_t src = base + s * L::STAGE;
+                        f2_store_2d(&tmOut, src, (kb0 + j) * F2_BK, tile * BM);
+                        f2_store_2d(&tmOut, src + F2_BOX, (kb0 + j) * F2_BK + 32, tile * BM);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (it > 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
+                        }
+                    }
+                    g += nblk;
+                }
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (it > 0) mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
         }
     } else if (warp < 12) {
         // ===================== update + A transform: thread = row of the tile = TMEM lane =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int grp = (warp - 4) >> 2;                          // K blocks with (it & 1) == grp
         const int row = (threadIdx.x - 128) & 127;
         const int sw = row & 7;
@@ -329,7 +407,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
         }
     } else if (warp < 16) {
         // ===================== epilogue: block accumulators -> FP32 register sums -> partial sums of the segment =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t it = 0;
@@ -341,6 +419,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
             for (int j = 0; j < BN; ++j) sum[j] = 0.f;
             for (int j = 0; j < nblk; ++j, ++it) {
                 const int acc = it & 1;
+                mbar_wait(bar_ready(it % F2_STAGES), (it / F2_STAGES) & 1);       // the block's A scales were written before this
                 mbar_wait(bar_tfull(acc), (it >> 1) & 1);
                 tc_fence_after();
                 const float sinv = sinv_ring[(it % F2_RING) * BM + row];
@@ -362,107 +441,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                                                                     sum[j + 2] * __ldg(p.binv + j + 2), sum[j + 3] * __ldg(p.binv + j + 3));
             g += nblk;
         }
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 16) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = make_idesc_f16<BN>();
-            const uint32_t total = (uint32_t)(R.g1 - R.g0);
-            for (uint32_t it = 0; it < total; ++it) {
-                const int s = it % F2_STAGES;
-                const uint32_t ph = (it / F2_STAGES) & 1;
-                const int acc = it & 1;
-                mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
-                mbar_wait(bar_ready(s), ph);
-                mbar_wait(bar_fullB(s), ph);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const int ta = it % F2_TA;
-                    const uint32_t d_tmem = tmem_base + acc * BN;
-                    const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta, a2 = a1 + 32;
-                    const uint64_t db1 = make_sw128_desc(base + s * L::STAGE + L::OFF_B1), db2 = make_sw128_desc(base + s * L::STAGE + L::OFF_B2);
-                    // cross terms a1.b2 + a2.b1 first, then D = a1.b1 + D * 2^-11 and the remaining main terms
-#pragma unroll
-                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        tc_mma_f16_ts(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
-                        tc_mma_f16_ts(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        if (kk == 0) tc_mma_f16_ts_scale11(d_tmem, a1, db1, idesc);
-                        else tc_mma_f16_ts(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
-                    }
-                    tc_commit(bar_emptyB(s));
-                    tc_commit(bar_aempty(ta));
-                    tc_commit(bar_tfull(acc));
-                }
-                __syncwarp();
-            }
-        } else if (warp == 17) {
-            // ===================== store issuer: updated tile -> 128 consecutive rows of b_out =====================
-            if (elect_one_sync()) {
-                uint32_t it = 0;
-                for (long long g = R.g0; g < R.g1;) {
-                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
-                    for (int j = 0; j < nblk; ++j, ++it) {
-                        const int s = it % F2_STAGES;
-                        mbar_wait(bar_ready(s), (it / F2_STAGES) & 1);
-                        const uint32_t src = base + s * L::STAGE;
-                        f2_store_2d(&tmOut, src, (kb0 + j) * F2_BK, tile * BM);
-                        f2_store_2d(&tmOut, src + F2_BOX, (kb0 + j) * F2_BK + 32, tile * BM);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        if (it > 0) {
-                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
-                        }
-                    }
-                    g += nblk;
-                }
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                if (it > 0) mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            }
-        } else if (warp == 18) {
-            // ===================== alpha planes (L2 resident) + table slices of the block =====================
-            if (elect_one_sync()) {
-                uint32_t it = 0;
-                for (long long g = R.g0; g < R.g1;) {
-                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
-                    const int a = p.tile_act[tile];
-                    const bool coef = p.dx[a] != 0;
-                    const float* obs_a = p.obs_tab + (size_t)((p.obs_per_action ? a : 0) * p.O) * p.Sp;
-                    const float* coef_a = p.coef + (size_t)a * 2 * p.Sp;
-                    for (int j = 0; j < nblk; ++j, ++it) {
-                        const int s = it % F2_STAGES;
-                        const uint32_t ph = (it / F2_STAGES) & 1;
-                        const int k0 = (kb0 + j) * F2_BK;
-                        const uint32_t st = base + s * L::STAGE;
-                        mbar_wait(bar_emptyB(s), ph ^ 1);
-                        mbar_expect_tx(bar_fullB(s), 2 * L::B_TILE);
-                        tma_load_2d(st + L::OFF_B1, &tmB1, k0, 0, bar_fullB(s));
-                        tma_load_2d(st + L::OFF_B2, &tmB2, k0, 0, bar_fullB(s));
-                        mbar_wait(bar_emptyA(s), ph ^ 1);
-                        mbar_expect_tx(bar_fullA(s), (uint32_t)(p.O + (coef ? 2 : 0)) * F2_BK * 4);
-                        for (int o = 0; o < p.O; ++o)
-                            f2_bulk_1d(st + L::OFF_TAB + o * F2_BK * 4, obs_a + (size_t)o * p.Sp + k0, F2_BK * 4, bar_fullA(s));
-                        if (coef) {
-                            f2_bulk_1d(st + L::OFF_TAB + F2_MAX_O * F2_BK * 4, coef_a + k0, F2_BK * 4, bar_fullA(s));
-                            f2_bulk_1d(st + L::OFF_TAB + (F2_MAX_O + 1) * F2_BK * 4, coef_a + p.Sp + k0, F2_BK * 4, bar_fullA(s));
-                        }
-                    }
-                    g += nblk;
-                }
-            }
-        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 19) {
+    if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }

@@ -17,6 +17,15 @@
 // (beliefs x pull tables, umma_gemm.cu store mode: 4·S bytes read per decision, no logarithm per state); a small finish
 // kernel adds the O(H + W) edge corrections and takes the first argmax.
 // v1 (OLFNAV_INFOTAXIS_V1=1, or more than 128 pull rows): one CTA per agent, one pass over the pushed belief per action.
+//
+// Accuracy.  ΔH_a is a difference of terms of order one (the entropy of the observation and its conditional entropy) while the gaps
+// between actions that decide the argmax can be 1e-6 and less on flat beliefs: FP32 sums (1e-6 relative) cannot settle those.
+// The finish kernel therefore combines the sums in float64, bounds its own error per action (E_a = kappa (1 + H_o + |Σ b C|)) and
+// lists the agents whose best two actions are closer than the bounds; infotaxis_exact_kernel re-derives THEIR choice in float64 in
+// the well-conditioned form      ΔH_a = corr_a + Σ_s b(s) · KL( O(.|R_a(s)) || p_a ) ,   KL >= 0 term by term,
+// (two passes over the agent's row per action: p_a first, then the sum).  A caller that asks for the ΔH values themselves (dH != NULL,
+// diagnostics and tests) gets the float64 kernel for every agent.  Decisions therefore agree with a float64 evaluation of the
+// reference's formula (agents/infotaxis_agent.py:257-293) except at ties below 1e-9 relative.
 #include "common.cuh"
 #include "stencil.cuh"
 #include "umma_gemm.cuh"
@@ -29,6 +38,7 @@ constexpr int IT_THREADS = 256;
 constexpr int IT_MAXO = 8;
 
 __device__ __forceinline__ float xlogx(float p) { return p > 0.f ? p * logf(p) : 0.f; }
+__device__ __forceinline__ double xlogx_d(double p) { return p > 0.0 ? p * log(p) : 0.0; }
 
 template <int NO>
 __global__ void __launch_bounds__(IT_THREADS)
@@ -108,15 +118,17 @@ infotaxis_kernel(const __grid_constant__ Geom g, const float* __restrict__ b, lo
 constexpr int IF_WARPS = 8;
 __global__ void __launch_bounds__(IF_WARPS * 32)
 infotaxis_finish_kernel(const __grid_constant__ Geom g, int n, const float* __restrict__ b, long long ld, const float* __restrict__ scale,
-                        const float* __restrict__ sums, int ld_sums, int* __restrict__ action, float* __restrict__ dH) {
+                        const float* __restrict__ sums, int ld_sums, int* __restrict__ action, float* __restrict__ dH,
+                        float kappa, int* __restrict__ unsure_rows, int* __restrict__ unsure_count) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * IF_WARPS + (threadIdx.x >> 5);
     if (row >= n) return;
     const float sc = scale ? scale[row] : 1.f;
     const float* bin = b + row * ld;
     const float* sm = sums + row * ld_sums;
-    float best = -INFINITY;
+    double best = -INFINITY, best_err = 0.0;
     int ba = -1;
+    double d_all[OLFNAV_MAX_ACTIONS], e_all[OLFNAV_MAX_ACTIONS];
     for (int a = 0; a < g.A; ++a) {
         const int dy = g.moves[a][0], dx = g.moves[a][1];
         // merge cells: a clipped axis with a non-zero move component; every cell of the downstream edge line receives itself
@@ -153,13 +165,160 @@ infotaxis_finish_kernel(const __grid_constant__ Geom g, int n, const float* __re
             }
             corr = warp_sum(corr);
         }
-        float plogp = 0.f;
-        for (int o = 0; o < g.O; ++o) plogp += xlogx(sm[a * (g.O + 1) + o] * sc);
-        const float d = -plogp + sm[a * (g.O + 1) + g.O] * sc + corr;
-        if (lane == 0 && dH) dH[row * g.A + a] = d;
-        if (best < d) { best = d; ba = a; }          // strict '<' : first maximum (infotaxis_agent.py:289)
+        // float64 combination of the FP32 sums.  Σ_o p_o = Σ_s b(s) exactly (Σ_o O_o = 1 everywhere), so the observation
+        // probabilities are renormalised by their own sum: the common relative bias of the tensor-core accumulation drops out.
+        double psum = 0.0;
+        for (int o = 0; o < g.O; ++o) psum += (double)sm[a * (g.O + 1) + o];
+        const double pinv = psum > 0.0 ? 1.0 / psum : 0.0;
+        double plogp = 0.0, habs = 0.0;
+        for (int o = 0; o < g.O; ++o) {
+            const double t = xlogx_d((double)sm[a * (g.O + 1) + o] * pinv);
+            plogp += t;
+            habs -= t;
+        }
+        const double bc = (double)sm[a * (g.O + 1) + g.O] * pinv;       // same bias as the p sums: divided out too
+        const double d = -plogp + bc + (double)corr;
+        d_all[a] = d;
+        e_all[a] = (double)kappa * (1.0 + habs + fabs(bc) + fabs((double)corr));
+        if (lane == 0 && dH) dH[row * g.A + a] = (float)d;
+        if (best < d) { best = d; best_err = e_all[a]; ba = a; }          // strict '<' : first maximum (infotaxis_agent.py:289)
     }
-    if (lane == 0) action[row] = ba;
+    if (lane == 0) {
+        action[row] = ba;
+        // another action within the error bounds of the best one: float64 re-evaluation (infotaxis_exact_kernel)
+        bool unsure = false;
+        for (int a = 0; a < g.A; ++a) unsure |= (a != ba) && (best - d_all[a] <= best_err + e_all[a]);
+        if (unsure && unsure_rows) unsure_rows[atomicAdd(unsure_count, 1)] = (int)row;
+    }
+}
+
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum of doubles, result in every thread; red holds >= 33 doubles
+template <int THREADS>
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum_d(v);
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = (lane < THREADS / 32) ? red[lane] : 0.0;
+        t = warp_sum_d(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    const double r = red[32];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ int bmove_d(int v, int d, int n, int wrap) {
+    v += d;
+    if (wrap) { if (v < 0) v += n; if (v >= n) v -= n; } else { v = max(0, min(n - 1, v)); }
+    return v;
+}
+
+// float64 evaluation of the infotaxis choice of the agents listed in `rows` (count on the device) or of every agent (rows == NULL).
+// One CTA per agent; per action two passes over the agent's row (L2 resident after the first): p_{a,o} = Σ_s b(s) O_o(R_a(s)), then
+// I_a = Σ_s b(s) [C(R_a(s)) - Σ_o O_o(R_a(s)) log p_{a,o}] (every KL term >= 0), plus the entropy change corr_a of the push at
+// clipped edges.  obs_ent64 holds C(s') = Σ_o O_o log O_o in double.
+__global__ void __launch_bounds__(IT_THREADS)
+infotaxis_exact_kernel(const __grid_constant__ Geom g, int n, const int* __restrict__ rows, const int* __restrict__ n_rows,
+                       const float* __restrict__ b, long long ld, const float* __restrict__ scale, const float* __restrict__ obs,
+                       const double* __restrict__ obs_ent64, int* __restrict__ action, float* __restrict__ dH) {
+    __shared__ double red[33];
+    __shared__ double s_logp[IT_MAXO];
+    __shared__ double s_dh[OLFNAV_MAX_ACTIONS];
+    if (rows && (int)blockIdx.x >= *n_rows) return;
+    const long long row = rows ? rows[blockIdx.x] : blockIdx.x;
+    if (row >= n) return;
+    const int tid = threadIdx.x;
+    const double sc = scale ? (double)scale[row] : 1.0;
+    const float* bin = b + row * ld;
+    const int total = g.H * g.Wp;
+    for (int a = 0; a < g.A; ++a) {
+        const int dy = g.moves[a][0], dx = g.moves[a][1];
+        const int ae = g.obs_per_action ? a : 0;
+        const float* ot = obs + (size_t)ae * g.O * g.Sp;
+        const double* ce = obs_ent64 + (size_t)ae * g.Sp;
+        double P[IT_MAXO];
+#pragma unroll
+        for (int o = 0; o < IT_MAXO; ++o) P[o] = 0.0;
+        for (int s = tid; s < total; s += IT_THREADS) {
+            const int y = s / g.Wp, x = s - y * g.Wp;
+            if (x >= g.W) continue;
+            const double v = (double)bin[s];
+            if (v == 0.0) continue;
+            const int s2 = bmove_d(y, dy, g.H, g.wrap_y) * g.Wp + bmove_d(x, dx, g.W, g.wrap_x);
+#pragma unroll
+            for (int o = 0; o < IT_MAXO; ++o)
+                if (o < g.O) P[o] += v * (double)__ldg(ot + (size_t)o * g.Sp + s2);
+        }
+#pragma unroll
+        for (int o = 0; o < IT_MAXO; ++o) {
+            if (o < g.O) {
+                const double p = block_sum_d<IT_THREADS>(P[o], red) * sc;
+                if (tid == 0) s_logp[o] = p > 0.0 ? log(p) : 0.0;
+            }
+        }
+        __syncthreads();
+        double acc = 0.0;
+        for (int s = tid; s < total; s += IT_THREADS) {
+            const int y = s / g.Wp, x = s - y * g.Wp;
+            if (x >= g.W) continue;
+            const double v = (double)bin[s];
+            if (v == 0.0) continue;
+            const int s2 = bmove_d(y, dy, g.H, g.wrap_y) * g.Wp + bmove_d(x, dx, g.W, g.wrap_x);
+            double t = ce[s2];
+#pragma unroll
+            for (int o = 0; o < IT_MAXO; ++o)
+                if (o < g.O) t -= (double)__ldg(ot + (size_t)o * g.Sp + s2) * s_logp[o];
+            acc += v * t;
+        }
+        // entropy change of the push: cells of the clipped downstream edge lines receive themselves and their upstream neighbours
+        double corr = 0.0;
+        const bool my = dy != 0 && !g.wrap_y && g.H > 1, mx = dx != 0 && !g.wrap_x && g.W > 1;
+        if (my || mx) {
+            const int ey = dy > 0 ? g.H - 1 : 0, ex = dx > 0 ? g.W - 1 : 0;
+            const int n_line_y = my ? g.W : 0, n_line_x = mx ? g.H : 0;
+            for (int k = tid; k < n_line_y + n_line_x; k += IT_THREADS) {
+                int y, x;
+                if (k < n_line_y) { y = ey; x = k; } else { y = k - n_line_y; x = ex; if (my && y == ey) continue; }
+                double tot = 0.0, parts = 0.0;
+                for (int sy = -1; sy <= 0; ++sy)
+                    for (int sx = -1; sx <= 0; ++sx) {
+                        const int ys = (sy == 0) ? y : y - dy, xs = (sx == 0) ? x : x - dx;
+                        if (sy == 0 && !(my && y == ey) && dy != 0) continue;
+                        if (sx == 0 && !(mx && x == ex) && dx != 0) continue;
+                        if (sy == -1 && dy == 0) continue;
+                        if (sx == -1 && dx == 0) continue;
+                        int yy = ys, xx = xs;
+                        if (g.wrap_y) { if (yy < 0) yy += g.H; if (yy >= g.H) yy -= g.H; } else if (yy < 0 || yy >= g.H) continue;
+                        if (g.wrap_x) { if (xx < 0) xx += g.W; if (xx >= g.W) xx -= g.W; } else if (xx < 0 || xx >= g.W) continue;
+                        const double v = (double)bin[(size_t)yy * g.Wp + xx] * sc;
+                        tot += v;
+                        parts += xlogx_d(v);
+                    }
+                corr += xlogx_d(tot) - parts;
+            }
+        }
+        const double d = block_sum_d<IT_THREADS>(acc * sc + corr, red);
+        if (tid == 0) s_dh[a] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double best = -INFINITY;
+        int ba = -1;
+        for (int a = 0; a < g.A; ++a) {
+            const double d = s_dh[a];
+            if (dH) dH[row * g.A + a] = (float)d;
+            if (best < d) { best = d; ba = a; }     // strict '<' : first maximum (infotaxis_agent.py:289)
+        }
+        action[row] = ba;
+    }
 }
 
 }  // namespace
@@ -173,17 +332,40 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
     cudaStream_t st = (cudaStream_t)stream;
     if (m->dense) return olf_dense_infotaxis(m, b, ld, n, scale, action, dH, st);
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_INFOTAXIS_V1"); return e && e[0] == '1'; }();
+    const bool exact_ok = m->obs_ent64 && m->g.O <= IT_MAXO;
+    if (dH && exact_ok && !force_v1) {
+        // the values themselves are asked for (diagnostics, tests): float64 for every agent
+        infotaxis_exact_kernel<<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, (int)n, nullptr, nullptr, b, ld, scale, m->obs, m->obs_ent64, action, dH);
+        OLF_LAUNCH_CHECK();
+        return OLFNAV_OK;
+    }
     if (!force_v1 && m->pull_rows <= 128) {
         const int ld_sums = m->pull_rows;
-        OlfScratch s_sums(st);
+        OlfScratch s_sums(st), s_list(st);
         OLF_CUDA(s_sums.alloc((size_t)n * ld_sums * sizeof(float)));
         float* sums = s_sums.as<float>();
+        int* list = nullptr;
+        if (exact_ok) {
+            OLF_CUDA(s_list.alloc(((size_t)n + 1) * sizeof(int)));
+            list = s_list.as<int>();
+            OLF_CUDA(cudaMemsetAsync(list + n, 0, sizeof(int), st));
+        }
+        // error bound of the FP32 path per unit of (1 + H_o + |Σ b C|): the split-precision GEMM is good to 1.2e-6 of Σ|a||b|
+        // (measured); OLFNAV_INFOTAXIS_KAPPA overrides (0 = never re-evaluate)
+        static const float kappa = [] { const char* e = getenv("OLFNAV_INFOTAXIS_KAPPA"); return e ? (float)atof(e) : 4e-6f; }();
         int rc = olf_umma_store(b, ld, n, m->g.Sp, m->pull_hi, m->pull_lo, m->pull_ld, m->pull_rows, sums, ld_sums, m->sm_count, st);
         if (rc == OLFNAV_OK) {
-            infotaxis_finish_kernel<<<olf_div_up(n, IF_WARPS), IF_WARPS * 32, 0, st>>>(m->g, (int)n, b, ld, scale, sums, ld_sums, action, dH);
+            infotaxis_finish_kernel<<<olf_div_up(n, IF_WARPS), IF_WARPS * 32, 0, st>>>(m->g, (int)n, b, ld, scale, sums, ld_sums, action, dH, kappa,
+                                                                                      kappa > 0.f ? list : nullptr, list ? list + n : nullptr);
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("infotaxis_choose: finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
+        if (rc == OLFNAV_OK && list && kappa > 0.f) {
+            infotaxis_exact_kernel<<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, (int)n, list, list + n, b, ld, scale, m->obs, m->obs_ent64, action, nullptr);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("infotaxis_choose: exact kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
+        }
+        if (rc == OLFNAV_OK && list && m->it_unsure) OLF_CUDA(cudaMemcpyAsync(m->it_unsure, list + n, sizeof(int), cudaMemcpyDeviceToDevice, st));
         return rc;
     }
     if (m->g.O > IT_MAXO) {
@@ -194,5 +376,16 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
     else if (m->g.O <= 5) infotaxis_kernel<5><<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, b, ld, scale, m->obs, m->obs_ent, action, dH);
     else                  infotaxis_kernel<8><<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, b, ld, scale, m->obs, m->obs_ent, action, dH);
     OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+// How many agents of the last olfnav_infotaxis_choose call on this model went through the float64 re-evaluation (synchronises the stream).
+extern "C" int olfnav_infotaxis_last_unsure(const olfnav_model* m, int32_t* count, void* stream) {
+    OLF_REQUIRE(m && count, "infotaxis_last_unsure: null argument");
+    *count = 0;
+    if (!m->it_unsure) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(m->device));
+    OLF_CUDA(cudaMemcpyAsync(count, m->it_unsure, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    OLF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return OLFNAV_OK;
 }

@@ -109,6 +109,7 @@ extern "C" int olfnav_model_create_padded(olfnav_model** out, int device, int H,
     const int Aeff = per_action ? A : 1;
 
     std::vector<float> h_obs((size_t)Aeff * O * Sp, 0.f), h_ent((size_t)Aeff * Sp, 0.f), h_rew((size_t)A * Sp, 0.f), h_start(Sp, 0.f);
+    std::vector<double> h_ent64((size_t)Aeff * Sp, 0.0);
     std::vector<uint8_t> h_end(Sp, 0);
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
@@ -123,6 +124,7 @@ extern "C" int olfnav_model_create_padded(olfnav_model** out, int device, int H,
                     if (pr > 0.0) c += pr * log(pr);
                 }
                 h_ent[(size_t)a * Sp + sp] = (float)c;
+                h_ent64[(size_t)a * Sp + sp] = c;
             }
             for (int a = 0; a < A; ++a) {
                 const int y2 = bmove(y, g.moves[a][0], H, wy), x2 = bmove(x, g.moves[a][1], W, wx);
@@ -174,6 +176,8 @@ extern "C" int olfnav_model_create_padded(olfnav_model** out, int device, int H,
     };
     up((void**)&m->obs, h_obs.data(), h_obs.size() * sizeof(float));
     up((void**)&m->obs_ent, h_ent.data(), h_ent.size() * sizeof(float));
+    up((void**)&m->obs_ent64, h_ent64.data(), h_ent64.size() * sizeof(double));
+    { const int zero = 0; up((void**)&m->it_unsure, &zero, sizeof(int)); }
     up((void**)&m->reward, h_rew.data(), h_rew.size() * sizeof(float));
     up((void**)&m->start, h_start.data(), h_start.size() * sizeof(float));
     up((void**)&m->end_mask, h_end.data(), h_end.size());
@@ -193,7 +197,7 @@ extern "C" int olfnav_model_create_padded(olfnav_model** out, int device, int H,
 extern "C" void olfnav_model_destroy(olfnav_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
+    cudaFree(m->obs); cudaFree(m->obs_ent); cudaFree(m->obs_ent64); cudaFree(m->it_unsure); cudaFree(m->reward); cudaFree(m->start); cudaFree(m->end_mask);
     cudaFree(m->pull_hi); cudaFree(m->pull_lo); cudaFree(m->coef); cudaFree(m->t_pull); cudaFree(m->t_push);
     delete m;
 }

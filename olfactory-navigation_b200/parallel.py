@@ -58,6 +58,23 @@ def run_test_sharded(agent, n: int, start_points: np.ndarray, time_shift: np.nda
     return out
 
 
+def assert_same_rng(rng: np.random.Generator, device) -> None:
+    '''
+    Sharded training keeps the host-side expand step replicated: every rank must draw the same numbers.  Compares a digest of the
+    generator state across the ranks (does not advance the generator) and raises on every rank if they differ.
+    '''
+    rank, ws = world()
+    if ws == 1:
+        return
+    import hashlib
+    import pickle
+    digest = int.from_bytes(hashlib.sha256(pickle.dumps(rng.bit_generator.state)).digest()[:7], 'little')
+    t = torch.tensor([digest, -digest], dtype=torch.int64, device=device if dist.get_backend() == 'nccl' else 'cpu')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if int(t[0]) != -int(t[1]):
+        raise RuntimeError('sharded training: the ranks hold different random generators (seed the agent / solver identically on every rank)')
+
+
 def all_gather_rows(rows: torch.Tensor, extra: torch.Tensor = None, counts: list = None):
     '''
     Concatenate a (k_r, D) tensor (k_r may differ per rank) over all ranks, plus an optional (k_r,) companion.
@@ -94,7 +111,7 @@ def all_gather_alphas(new_alpha: torch.Tensor, actions: torch.Tensor):
     return all_gather_rows(new_alpha, actions)
 
 
-def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: int = 0, exchange: str = 'indices'):
+def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: int = 0, exchange: str = 'indices', return_values: bool = False):
     '''
     One PBVI backup with the belief points split across ranks: each rank runs the selection GEMM (argmax over the alpha set for
     every (belief, action, observation)) on rows [lo, hi) of the (replicated) belief set.  Returns (new_alpha, best_a) for ALL
@@ -104,23 +121,34 @@ def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: 
     (1 + A*O) ints — and every rank assembles all B new vectors from its own copy of Gamma (a streaming kernel, ~1 ms for
     10 000 points): 0.5 MB on the wire instead of B x Sp floats (1.2 GB at C3).  exchange='alphas': all-gather the assembled
     vectors (the first implementation; kept for comparison).  Both give bit-identical results (same Gamma, same indices).
+    return_values=True also returns the value of every new vector at its belief point (gathered with the selection; FSVI / HSVI
+    keep a new vector only where it improves on the current value function).
     '''
     from .pomdp import BeliefSet
     from .solvers import backup_device, backup_select_device, backup_assemble_device
     rank, ws = world()
     lo, hi = shard_bounds(len(belief_set), rank, ws)
     part = BeliefSet(model, _buffers=(belief_set._b[lo:hi], belief_set._scale[lo:hi], hi - lo), device=belief_set.device)
+    counts = [b - a for a, b in (shard_bounds(len(belief_set), r, ws) for r in range(ws))]
     if exchange == 'alphas' or ws == 1:
         if hi > lo:
-            new_alpha, best_a, _, _ = backup_device(model, part, alphas, gamma, path)
+            new_alpha, best_a, best_v, _ = backup_device(model, part, alphas, gamma, path)
         else:
             new_alpha = torch.empty((0, alphas.shape[1]), dtype=alphas.dtype, device=alphas.device)
             best_a = torch.empty(0, dtype=torch.int32, device=alphas.device)
-        return all_gather_alphas(new_alpha, best_a)
+            best_v = torch.empty(0, dtype=torch.float32, device=alphas.device)
+        out_alpha, out_a = all_gather_alphas(new_alpha, best_a)
+        if not return_values:
+            return out_alpha, out_a
+        out_v = all_gather_rows(best_v[:, None], counts=counts)[0][:, 0].contiguous() if ws > 1 else best_v
+        return out_alpha, out_a, out_v
     G = alphas.shape[0]
-    gam, best_g, best_a, _ = backup_select_device(model, part, alphas, gamma, path)
-    packed = torch.cat([best_a[:, None], best_g.reshape(hi - lo, -1)], dim=1).contiguous()       # (B_r, 1 + A*O) int32
-    packed_all, _ = all_gather_rows(packed, counts=[b - a for a, b in (shard_bounds(len(belief_set), r, ws) for r in range(ws))])
+    gam, best_g, best_a, best_v = backup_select_device(model, part, alphas, gamma, path)
+    # (B_r, 2 + A*O) int32: best action, the value's bit pattern, the alpha indices
+    packed = torch.cat([best_a[:, None], best_v.view(torch.int32)[:, None], best_g.reshape(hi - lo, -1)], dim=1).contiguous()
+    packed_all, _ = all_gather_rows(packed, counts=counts)
     best_a_all = packed_all[:, 0].contiguous()
-    best_g_all = packed_all[:, 1:].contiguous()
-    return backup_assemble_device(model, gam, G, best_g_all, best_a_all, belief_set.device), best_a_all
+    best_v_all = packed_all[:, 1].contiguous().view(torch.float32)
+    best_g_all = packed_all[:, 2:].contiguous()
+    new_alpha = backup_assemble_device(model, gam, G, best_g_all, best_a_all, belief_set.device)
+    return (new_alpha, best_a_all, best_v_all) if return_values else (new_alpha, best_a_all)

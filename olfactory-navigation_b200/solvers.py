@@ -16,6 +16,7 @@ identical generators give identical (action, observation) sequences.
 '''
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -210,6 +211,13 @@ class _PBVI:
         rng = np.random.default_rng() if rng is None else rng
         device = current_device()
         dev = torch.device('cuda', device)
+        # Under torchrun (one process per GPU, process group initialised) the backups of this solve are sharded over the ranks.
+        # The expand step draws on the host: every rank must hold the same generator state (same seed), so that all ranks select the
+        # same belief points — checked once per solve through the first draw.
+        from . import parallel
+        sharded = parallel.world()[1] > 1 and os.environ.get('OLFNAV_SHARDED_TRAIN', '1') != '0'
+        if sharded:
+            parallel.assert_same_rng(rng, dev)
         hist = SolverHistory(model, history_tracking_level, gamma, eps, cls.name)
         t_start = time.perf_counter()
         extra = cls.prepare(model, gamma, eps, print_progress, use_reachability=use_reachability, **flavour)
@@ -247,7 +255,12 @@ class _PBVI:
             for _ in range(update_passes):
                 if len(target) == 0:
                     break
-                new_alpha, best_a, new_v, _ = backup_device(model, target, alphas, gamma, gemm_path)
+                if sharded:
+                    # belief points split across the ranks of the process group, selection all-gathered (parallel.backup_sharded):
+                    # every rank ends up with the same new vectors, bit-identical to the single-GPU backup
+                    new_alpha, best_a, new_v = parallel.backup_sharded(model, target, alphas, gamma, gemm_path, return_values=True)
+                else:
+                    new_alpha, best_a, new_v, _ = backup_device(model, target, alphas, gamma, gemm_path)
                 if cls.dominance_prune:
                     keep = new_v > values_of(target, alphas, actions)
                     new_alpha, best_a = new_alpha[keep], best_a[keep]
@@ -615,6 +628,13 @@ class Perseus(_PBVI):
         rng = np.random.default_rng() if rng is None else rng
         device = current_device()
         dev = torch.device('cuda', device)
+        # Under torchrun (one process per GPU, process group initialised) the backups of this solve are sharded over the ranks.
+        # The expand step draws on the host: every rank must hold the same generator state (same seed), so that all ranks select the
+        # same belief points — checked once per solve through the first draw.
+        from . import parallel
+        sharded = parallel.world()[1] > 1 and os.environ.get('OLFNAV_SHARDED_TRAIN', '1') != '0'
+        if sharded:
+            parallel.assert_same_rng(rng, dev)
         hist = SolverHistory(model, history_tracking_level, gamma, eps, cls.name)
         t_start = time.perf_counter()
         if initial_belief is None:

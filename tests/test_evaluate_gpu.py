@@ -204,12 +204,17 @@ def test_tail_split_of_the_last_wave(G):
         c = onb.synthetic.config('C1')
         it = onb.agents.Infotaxis_Agent(agent.environment, thresholds=c['thresholds'])
         it.initialize_state(n, onb.BeliefSet(it.model, _buffers=(bs._b.clone(), bs._scale.clone(), n), device=0))
-        ids_all = it.choose_action_device(return_delta_H=True).clone()
-        dh_all = it.last_delta_H.clone()
+        # production path (FP32 tensor-core sums through the tail split + float64 re-evaluation of near ties) against the float64
+        # kernel: the same decisions, in the large batch and in the small one
+        ids_all = it.choose_action_device().clone()
+        ids_all_exact = it.choose_action_device(return_delta_H=True).clone()
+        dh = it.last_delta_H.double().cpu().numpy()
+        srt = np.sort(dh, axis=1)
+        clear = torch.as_tensor((srt[:, -1] - srt[:, -2]) > 1e-6 * np.abs(dh).max(1), device=ids_all.device)
+        assert bool((ids_all == ids_all_exact)[clear].all())
         it.initialize_state(1200, onb.BeliefSet(it.model, _buffers=(bs._b[n - 1200:n].clone(), bs._scale[n - 1200:n].clone(), 1200), device=0))
-        ids_t = it.choose_action_device(return_delta_H=True)
-        np.testing.assert_allclose(dh_all[n - 1200:].cpu().numpy(), it.last_delta_H.cpu().numpy(), rtol=1e-4, atol=1e-5)
-        assert float((ids_all[n - 1200:] == ids_t).float().mean()) > 0.99
+        ids_t = it.choose_action_device()
+        assert bool((ids_all[n - 1200:] == ids_t)[clear[n - 1200:]].all())
 
 
 def test_tail_split_in_the_backup_gemm():
