@@ -33,9 +33,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIG = 'C2'
+POLICY = 'fsvi'             # 'infotaxis' for --config C4
+MAIN = 'steps'              # 'backup' for --config C3
 N_AGENTS = 100_000
 WORKLOADS = {'C2': '55x247 plume + 14/62 margins = 83x371 = 30793 states, 4 actions, 3 observations, wrap_vertical',
              'C5': '110x494 plume + 28/124 margins = 166x742 = 123172 states, 4 actions, 3 observations, wrap_vertical'}
+# DRAM bytes per updated agent from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch / rows updated)
+TRAFFIC = {}
 TRAIN = dict(expansions=10)          # the reference notebook's FSVI training call (experiments/pomdp_agent_training.ipynb cell 4)
 
 
@@ -46,8 +50,10 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--agents', type=int, default=None, help='agents per GPU (default: 100 000 for C2, 125 000 for C5)')
-    ap.add_argument('--config', default='C2', choices=['C2', 'C5'],
-                    help='C2 = BASELINE configs[1] (the metric\'s configuration, default); C5 = configs[4], the 2x-resolution plume of the scaling sweep (10^6 agents over 8 GPUs)')
+    ap.add_argument('--config', default='C2', choices=['C2', 'C3', 'C4', 'C5'],
+                    help='C2 = BASELINE configs[1] (the metric\'s configuration, default); C3 = configs[2], PBVI backups of 10 000 belief points '
+                         '(the line\'s value is belief-backups/s at --backup-alphas, FSVI training wall time reported next to it); '
+                         'C4 = configs[3], Infotaxis agent on the C2 plume; C5 = configs[4], the 2x-resolution plume of the scaling sweep (10^6 agents over 8 GPUs)')
     ap.add_argument('--cpu-agents', type=int, default=None, help='agents of the bounded CPU sample (default: 256 for C2, 64 for C5: same CPU work per sample)')
     ap.add_argument('--cpu-steps', type=int, default=12)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -55,8 +61,10 @@ def parse():
     ap.add_argument('--backup-points', type=int, default=10_000)
     ap.add_argument('--backup-alphas', type=int, default=512)
     args = ap.parse_args()
-    global CONFIG
-    CONFIG = args.config
+    global CONFIG, POLICY, MAIN
+    MAIN = 'backup' if args.config == 'C3' else 'steps'
+    POLICY = 'infotaxis' if args.config == 'C4' else 'fsvi'
+    CONFIG = 'C5' if args.config == 'C5' else 'C2'          # C3 and C4 run on the C2 plume
     if args.agents is None:
         args.agents = N_AGENTS if CONFIG == 'C2' else 125_000
     if args.cpu_agents is None:
@@ -106,6 +114,21 @@ class ClockSampler:
 
 # =================================================================================================
 _CPU_SETUP = None
+_SYN = None
+
+
+def synthetic_module():
+    '''
+    The synthetic plume generator, loaded by file path: it is pure NumPy, and importing it through the package would dlopen
+    libolfnav_b200.so (the package __init__ loads the library) — the CPU reference arm must not map any of the repo's native code.
+    '''
+    global _SYN
+    if _SYN is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('_olfnav_synthetic', os.path.join(ROOT, 'olfactory-navigation_b200', 'synthetic.py'))
+        _SYN = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_SYN)
+    return _SYN
 
 
 def cpu_threads() -> int:
@@ -130,7 +153,7 @@ def cpu_setup():
     from oracle import refloader
     refloader.install_oracle_toolkit()
     from oracle import sim
-    import olfactory_navigation_b200.synthetic as syn
+    syn = synthetic_module()
     c = syn.CONFIGS[CONFIG]
     data = syn.plume_frames(c['T'], c['h'], c['w'], source_y=c['source'][0], seed=syn.SEED)
     thr = np.array([-np.inf, c['thresholds'], np.inf])
@@ -150,7 +173,7 @@ def oracle_value_function(G_target: int = None):
     'The value function of the reference arm, trained without a GPU: the oracle\'s own FSVI with the bench\'s training call (untimed setup).'
     sim, setup = cpu_setup()
     import pomdp_toolkit as tk
-    import olfactory_navigation_b200.synthetic as syn
+    syn = synthetic_module()
     vf = tk.solvers.FSVI.solve(setup['model'], gamma=0.99, eps=1e-6, rng=np.random.default_rng(syn.SEED), print_progress=False, **TRAIN)[0]
     return vf.alpha_vector_array, vf.actions
 
@@ -249,10 +272,26 @@ def run_ours(args) -> None:
     # ---- workload: environment, trained agent (untimed) --------------------------------------------
     c = onb.synthetic.config(CONFIG)
     env = onb.Environment(**c['env_kwargs'])
-    agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
-    agent.train(print_progress=False, print_stats=False, **TRAIN)
-    G = len(agent.value_function)
+    if POLICY == 'infotaxis':
+        agent = onb.agents.Infotaxis_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+        G, train_s = 0, None
+    else:
+        # FSVI training through the Agent API (under torchrun every backup of the solve is sharded over the ranks, the selection
+        # all-gathered with NCCL); timed once after a warm-up training, wall clock between device synchronisations
+        agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+        agent.train(print_progress=False, print_stats=False, **TRAIN)
+        agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t_train = time.perf_counter()
+        agent.train(print_progress=False, print_stats=False, **TRAIN)
+        torch.cuda.synchronize(dev)
+        train_s = time.perf_counter() - t_train
+        G = len(agent.value_function)
     model = agent.model
+    fused = (POLICY == 'fsvi' and os.environ.get('OLFNAV_FUSED_STEP', '1') != '0'
+             and lib.olfnav_can_fuse_policy(model.handle(local), agent.value_function.handle(local)) == 1)
     S = model.state_count
     n = args.agents
     rng = np.random.default_rng(onb.synthetic.SEED + 17 * rank)         # every rank simulates its own shard of agents
@@ -343,33 +382,61 @@ def run_ours(args) -> None:
     if rank == 0:
         peak, peak_src = measured_peaks()
         ach = sum(bs_bytes) / (sum(bs_ms) * 1e-3) / 1e9 if sum(bs_ms) > 0 else 0.0
+        Sp = model.padded_states
+        if fused:
+            kernel = 'fused2_kernel<%d>' % ((G + 15) // 16 * 16)
+            evaluate_path = 'inside the update kernel (tcgen05 fp16x2-split, A operand = the updated row)'
+            what = ('one-pass belief update + policy: 8*S algorithmic bytes per agent-step for BOTH (read b, write b\'); the CUDA events '
+                    'bracket the plan kernels, fused2_kernel and the finishing kernel')
+        else:
+            kernel = 'belief_step_tma_kernel<256>'
+            evaluate_path = ('infotaxis: tcgen05 3xtf32 sums + float64 re-evaluation of near ties' if POLICY == 'infotaxis' else
+                             'simt-fp32' if G <= 8 else ('tcgen05-fp16x2-split' if (G >= 64 and os.environ.get('OLFNAV_GEMM_F16', '1') != '0') else 'tcgen05-3xtf32'))
+            what = 'belief update alone: 8*S algorithmic bytes per agent-step; the policy is a second pass (4*S more bytes), see evaluate_ms_per_step'
+        traffic_per_agent, traffic_src = TRAFFIC.get('fused2' if fused else 'belief_step', (None, None))
+        label = {'fsvi': 'run_test of a trained FSVI agent', 'infotaxis': 'run_test of an Infotaxis agent (BASELINE configs[3])'}[POLICY]
         line = {
             'metric': 'agent_belief_steps_per_s', 'value': agent_steps / (elapsed_ms * 1e-3), 'unit': 'agent-steps/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG} run_test of a trained FSVI agent: ' + WORKLOADS[CONFIG],
-                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': 'simt-fp32' if G <= 8 else ('tcgen05-fp16x2-split' if (G >= 64 and os.environ.get('OLFNAV_GEMM_F16', '1') != '0') else 'tcgen05-3xtf32'),
+            'config': {'workload': f'{args.config} {label}: ' + WORKLOADS[CONFIG],
+                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': evaluate_path, 'one_pass_step': bool(fused),
                        'sharding': 'agents split across ranks, no data-path collective',
-                       'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * model.padded_states * 4 / 1e9)},
+                       'layout': 'grid rows padded to %d floats (%d padded states for %d states)' % (model.padded_width, Sp, S),
+                       'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * Sp * 4 / 1e9)},
             'e2e': {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'setup_ms_outside_value': setup_ms,
             'clocks': clk,
-            'roofline': {'kernel': 'belief_step_tma_kernel<256>', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                         # ncu --set full, profiles/r1q_ncu_full_raw_belief_step_and_umma_ts.csv: dram read 12.352 GB + write 12.292 GB per launch of 100 000 rows
-                         # at 99 953 updated rows = 246 442 B per updated agent (algorithmic 246 344 B): scaled to this run's launches
-                         'traffic': 246438.8 * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if bs_bytes else None,
-                         'traffic_unit': 'bytes per launch (ncu r1q capture, scaled by updated rows)', 'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
+            'roofline': {'kernel': kernel, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'what': what,
+                         # DRAM bytes per launch: a constant recorded from one ncu --set full capture of this kernel (file named in
+                         # traffic_source), scaled by the rows this run's launches updated — not measured by this run
+                         'traffic': traffic_per_agent * (sum(bs_bytes) / (8.0 * S)) / max(len(bs_bytes), 1) if (bs_bytes and traffic_per_agent) else None,
+                         'traffic_unit': 'bytes per launch (recorded ncu constant x updated rows)', 'traffic_source': traffic_src,
+                         'peak_source': peak_src, 'algorithmic_bytes_per_agent_step': 8 * S,
+                         'step_frac_of_8S_bound': (8.0 * S * agent_steps / world) / (elapsed_ms * 1e-3) / 1e9 / peak,
                          'share_of_step': sum(bs_ms) / elapsed_ms, 'evaluate_ms_per_step': statistics.mean(ev_ms) if ev_ms else None,
                          'belief_step_ms_per_step': statistics.mean(bs_ms) if bs_ms else None},
         }
+        if train_s is not None:
+            line['training'] = {'wall_s': train_s, 'call': 'FSVI_Agent.train(expansions=10)', 'alpha_vectors': G, 'n_gpus': world,
+                                'sharded_backups': world > 1}
         if backup is not None:
             line['backup'] = backup
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and POLICY == 'fsvi':
             vf = agent.value_function
             r = cpu_sample(vf.alpha_vector_array, vf.actions, args.cpu_agents, args.cpu_steps)
             line['cpu_baseline'] = {'value': r['per_s'], 'unit': 'agent-steps/s', 'cores': cpu_threads(), 'kind': 'port',
                                     'sample': f'oracle/sim.py (NumPy fp64 restatement of the reference loop) on {args.cpu_agents} agents x {args.cpu_steps} steps '
                                               f'of the same model and value function (G={G}); {r["agent_steps"]} agent-steps in {r["seconds"]:.1f} s; single process, BLAS threads'}
+        if MAIN == 'backup' and backup is not None:
+            # --config C3: the backup is the line; the stepping numbers ride along
+            steps_line = {k: line[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'e2e', 'roofline')}
+            line.update({'metric': 'pbvi_belief_backups_per_s', 'value': backup['value'], 'unit': backup['unit'], 'ms_per_step': backup['ms_per_backup'],
+                         'scaling': 'strong', 'roofline': backup['roofline'], 'stepping': steps_line})
+            line['config']['workload'] = (f'C3 PBVI backup of {backup["belief_points"]} belief points against {backup["alpha_vectors"]} alpha vectors on the C2 plume '
+                                          f'({WORKLOADS[CONFIG]}); belief points split across the ranks, selection all-gathered')
+            line['e2e'] = {'value': backup['value'], 'unit': backup['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                           'note': 'belief points and alpha vectors are device resident in training: the backup has no host leg'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

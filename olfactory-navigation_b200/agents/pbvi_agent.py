@@ -62,15 +62,35 @@ class BeliefSimulationMixin:
         self._cur = 0
         self._n_live = n
         self._ok = torch.empty(cap, dtype=torch.uint8, device=dev)
+        self._row_map = None             # set by run_test while the rows are grouped by action (see _rows_to_agent_order)
         self._action_ids = None          # device int32 (n_live,), set by choose_action
         self._dropped = None             # bool (n,) rows the last update dropped (source reached)
         self._moves_dev = torch.as_tensor(np.ascontiguousarray(self.action_set), dtype=torch.int32, device=dev).contiguous()
         self.action_played = None
         self.succeeded_update = None
 
+    def _rows_to_agent_order(self) -> None:
+        '''
+        run_test's one-pass step kernel leaves the live belief rows grouped by action, with a row map (agent i -> row): gather them
+        back into agent order (row i = agent i) the first time anything else looks at the state.
+        '''
+        row_map = getattr(self, '_row_map', None)
+        if row_map is None or getattr(self, '_bufs', None) is None:
+            self._row_map = None
+            return
+        self._row_map = None
+        m = self._n_live
+        if m:
+            src, dst = self._cur, 1 - self._cur
+            with torch.cuda.device(self._device):
+                check(lib.olfnav_copy_rows(ptr(self._bufs[src]), ptr(self._bufs[dst]), self._bufs[src].stride(0), self.model.padded_states,
+                                           ptr(row_map), ptr(self._scales[src]), ptr(self._scales[dst]), m, stream()))
+            self._cur = dst
+
     # -- views ----------------------------------------------------------------------------------
     @property
     def belief(self) -> BeliefSet | None:
+        self._rows_to_agent_order()
         if getattr(self, '_bufs', None) is None or self._n_live == 0:
             return None
         return BeliefSet(self.model, _buffers=(self._bufs[self._cur], self._scales[self._cur], self._n_live), device=self._device)
@@ -91,6 +111,7 @@ class BeliefSimulationMixin:
         the update was impossible (normaliser 0).  Agents with reached=True are dropped and MUST be
         killed by the caller (the reference's run_test always does: simulation.py:1480-1497).
         '''
+        self._rows_to_agent_order()
         n = self._n_live
         assert self._action_ids is not None and len(self._action_ids) == n, 'choose_action must be called before update_state'
         dev = obs_ids.device
@@ -115,6 +136,7 @@ class BeliefSimulationMixin:
 
     def kill_device(self, to_kill: torch.Tensor) -> None:
         'to_kill bool (n,) in the indexing used by the last update_state_device call.'
+        self._rows_to_agent_order()
         dropped = self._dropped if self._dropped is not None else torch.zeros_like(to_kill)
         self._dropped = None
         if bool((dropped & ~to_kill).any()):

@@ -46,7 +46,8 @@ int olf_make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t
 namespace {
 
 constexpr int F2_BK = 64;                  // states per K block
-constexpr int F2_STAGES = 4;
+constexpr int F2_STAGES = 5;                // A ring: gathered rows (updated in place) + table slices of a K block
+constexpr int F2_BSTAGES = 2;               // B ring: the two FP16 alpha-plane tiles of a K block (L2 resident, consumed by the MMAs only)
 constexpr int F2_TA = 4;                   // TMEM slots of the A operand
 constexpr int F2_THREADS = 512;
 constexpr int F2_BOX = BM * 128;           // bytes of one 32-float box of 128 rows
@@ -59,7 +60,8 @@ constexpr int F2_PLAN_ITEMS = 4096;        // agents per CTA of the plan kernels
 
 struct F2Params {
     const float* b_in; long long ld;
-    int KB, Sp, Wp;
+    int KB, Sp, Wp, W;
+    int dbg;                               // OLFNAV_F2_DBG ablation bits: 1 no stores, 2 no MMAs, 4 no tensor-memory writes, 8 no update arithmetic, 16 no halo loads
     int n_tiles_max; const int* n_tiles_dev;
     const int* tile_act;                   // [n_tiles_max]
     const int* slot_src;                   // [n_tiles_max * 128] belief row in b_in, -1 = empty slot
@@ -77,45 +79,132 @@ struct F2Params {
 template <int BN>
 struct F2Layout {
     static constexpr int B_TILE = BN * 128;                     // one FP16 plane tile: BN rows x 64 halfs
-    static constexpr int STAGE = F2_A_BYTES + 2 * B_TILE + F2_TAB_BYTES;
-    static constexpr int OFF_B1 = F2_A_BYTES, OFF_B2 = F2_A_BYTES + B_TILE, OFF_TAB = F2_A_BYTES + 2 * B_TILE;
-    static constexpr int OFF_SINV = F2_STAGES * STAGE;          // [F2_RING][128] floats
-    static constexpr int OFF_BARS = OFF_SINV + F2_RING * BM * 4;
-    static constexpr int NUM_BARS = 5 * F2_STAGES + F2_TA + 4;
+    static constexpr int STAGE = F2_A_BYTES + F2_TAB_BYTES;     // A ring stage
+    static constexpr int OFF_TAB = F2_A_BYTES;
+    static constexpr int BSTAGE = 2 * B_TILE;                   // B ring stage: plane 1, plane 2
+    static constexpr int OFF_B = F2_STAGES * STAGE;
+    static constexpr int OFF_SINV = OFF_B + F2_BSTAGES * BSTAGE;   // [F2_RING][128] floats
+    static constexpr int OFF_EDGE = OFF_SINV + F2_RING * BM * 4;      // [F2_RING][128] floats: raw boundary element of a block (x moves)
+    static constexpr int OFF_BARS = OFF_EDGE + F2_RING * BM * 4;
+    static constexpr int NUM_BARS = 3 * F2_STAGES + 2 * F2_BSTAGES + F2_TA + 4 + F2_RING;
     static constexpr int TOTAL = OFF_BARS + 8 * NUM_BARS + 16 + 1024;
     static constexpr int A_BASE = 256;                          // TMEM: [0, 2 BN) accumulators, [256 + 64 t, +64) A slot t
+    static_assert((STAGE % 1024) == 0 && (BSTAGE % 1024) == 0 && (B_TILE % 1024) == 0, "swizzled tiles start on 1024-byte boundaries");
     static_assert(2 * BN <= A_BASE && A_BASE + 64 * F2_TA <= 512, "tensor memory budget");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ void f2_gather4(uint32_t dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                 :: "r"(dst), "l"(map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+// L2 policies: the belief rows stream through once (evict first), the alpha planes and table slices are re-read by every tile
+// (evict last).  Without them the 25 GB of rows that pass through the 126 MB L2 per step push the 10 MB of planes out between two
+// uses: measured 15.9 GB of DRAM reads per launch for 12.7 GB of rows (ncu r2j).
+__device__ __forceinline__ uint64_t f2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t f2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void f2_gather4(uint32_t dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void f2_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void f2_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" :: "l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void f2_bulk_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void f2_bulk_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 
-// The CTAs split the sequence of (tile, K block) pairs evenly: CTA c owns the global blocks [g0, g1).
-struct F2Range {
-    long long g0, g1, per;
-    int n_tiles;
+// Work units.  Every CTA walks the K blocks of a tile from 0 upwards, and the CTAs of a wave do so together: the streams of
+// the 148 tiles in flight then touch the same column range of their rows at the same time, which is what HBM wants for this pattern
+// (scripts/gather_stream_bench.cu: 5.4-5.6 TB/s in lockstep against 4.8-5.1 TB/s with staggered K positions; a stream-K split of
+// the (tile, K block) sequence staggers them and cost 12-27 %).  Tiles [0, full_units) are whole units; the tiles of the last,
+// partial wave are cut along K into `split` parts each so that the wave is spread over all SMs (unit full_units + t * split + q).
+// Every unit writes its FP32 partial sums and its share of the normalisers to slot `unit` of the workspaces.
+struct F2Work {
+    int n_tiles, full_units, split, per, num_units, KB;
+    __device__ __forceinline__ void init(const F2Params& p) {
+        const int nt = *p.n_tiles_dev;
+        n_tiles = nt < p.n_tiles_max ? nt : p.n_tiles_max;
+        KB = p.KB;
+        const int grid = (int)gridDim.x;
+        full_units = (n_tiles / grid) * grid;
+        const int tail = n_tiles - full_units;
+        split = tail ? (grid / tail < 8 ? grid / tail : 8) : 1;
+        if (split < 1) split = 1;
+        per = (KB + split - 1) / split;
+        num_units = full_units + tail * split;
+    }
+    __device__ __forceinline__ void unit(int u, int& tile, int& kb0, int& nblk) const {
+        if (u < full_units) { tile = u; kb0 = 0; nblk = KB; return; }
+        const int t = (u - full_units) / split, q = (u - full_units) - t * split;
+        tile = full_units + t;
+        kb0 = q * per < KB ? q * per : KB;
+        nblk = per < KB - kb0 ? per : KB - kb0;
+    }
 };
-__device__ __forceinline__ F2Range f2_range(const F2Params& p) {
-    F2Range r;
-    int nt = *p.n_tiles_dev;
-    r.n_tiles = nt < p.n_tiles_max ? nt : p.n_tiles_max;
-    const long long total = (long long)r.n_tiles * p.KB;
-    r.per = (total + gridDim.x - 1) / gridDim.x;
-    r.g0 = (long long)blockIdx.x * r.per;
-    if (r.g0 > total) r.g0 = total;
-    r.g1 = r.g0 + r.per;
-    if (r.g1 > total) r.g1 = total;
-    return r;
+
+// The update of one row segment (64 states of one agent, thread-private): raw values from the 128B-swizzled tile, updated values
+// written back in place and kept in bp[].  DX = x component of the tile's move (compile time: the one-cell shift is a register
+// rename); MASKED = the block touches a clipped edge of the grid row or its padding (0 / 1 masks cA, cB from the table slices),
+// otherwise every cell simply takes its upstream neighbour.  (v * sc) * O in this order: bit-identical to belief_step_tma_kernel.
+template <int DX, bool MASKED>
+__device__ __forceinline__ void f2_update(uint8_t* rowp, int sw, const float* lik, const float* cA, const float* cB, float sc, float halo,
+                                          float (&bp)[F2_BK], float& zacc, float& mx) {
+    if constexpr (DX == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float4* q = reinterpret_cast<float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4));
+            const float4 v = *q;
+            const float4 l = *reinterpret_cast<const float4*>(lik + 4 * c);
+            float4 r;
+            r.x = v.x * sc * l.x; r.y = v.y * sc * l.y; r.z = v.z * sc * l.z; r.w = v.w * sc * l.w;
+            *q = r;
+            zacc += (r.x + r.y) + (r.z + r.w);
+            mx = fmaxf(fmaxf(mx, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
+            bp[4 * c] = r.x; bp[4 * c + 1] = r.y; bp[4 * c + 2] = r.z; bp[4 * c + 3] = r.w;
+        }
+    } else {
+        float v[F2_BK];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4));
+            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 l = *reinterpret_cast<const float4*>(lik + 4 * c);
+            const float la[4] = {l.x, l.y, l.z, l.w};
+            float ca[4] = {1.f, 1.f, 1.f, 1.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (MASKED) {
+                const float4 ma = *reinterpret_cast<const float4*>(cA + 4 * c);
+                const float4 mb = *reinterpret_cast<const float4*>(cB + 4 * c);
+                ca[0] = ma.x; ca[1] = ma.y; ca[2] = ma.z; ca[3] = ma.w;
+                cb[0] = mb.x; cb[1] = mb.y; cb[2] = mb.z; cb[3] = mb.w;
+            }
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = 4 * c + e;
+                // value arriving from one cell back along the move (k - DX), from the halo across the block boundary
+                const float nb = DX > 0 ? (k == 0 ? halo : v[k > 0 ? k - 1 : 0]) : (k == F2_BK - 1 ? halo : v[k < F2_BK - 1 ? k + 1 : k]);
+                const float w = MASKED ? fmaf(ca[e], nb, cb[e] * v[k]) : nb;     // masks are 0 / 1: exact, one rounding for the merged cell
+                r[e] = w * sc * la[e];
+            }
+            *reinterpret_cast<float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4)) = make_float4(r[0], r[1], r[2], r[3]);
+            zacc += (r[0] + r[1]) + (r[2] + r[3]);
+            mx = fmaxf(fmaxf(mx, fmaxf(r[0], r[1])), fmaxf(r[2], r[3]));
+            bp[4 * c] = r[0]; bp[4 * c + 1] = r[1]; bp[4 * c + 2] = r[2]; bp[4 * c + 3] = r[3];
+        }
+    }
 }
 
 template <int BN>
@@ -128,26 +217,27 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + L::OFF_BARS;
     auto bar_fullA = [&](int s) { return bars + 8 * s; };                       // gathered rows + table slices landed (2 producers)
-    auto bar_fullB = [&](int s) { return bars + 8 * (F2_STAGES + s); };         // alpha planes landed
-    auto bar_ready = [&](int s) { return bars + 8 * (2 * F2_STAGES + s); };     // row updated in place, A operand in tensor memory
-    auto bar_emptyA = [&](int s) { return bars + 8 * (3 * F2_STAGES + s); };    // the stores of the tile have read it
-    auto bar_emptyB = [&](int s) { return bars + 8 * (4 * F2_STAGES + s); };    // the MMAs of the block have retired
-    auto bar_aempty = [&](int t) { return bars + 8 * (5 * F2_STAGES + t); };    // TMEM A slot t read by its MMAs
-    auto bar_tfull = [&](int a) { return bars + 8 * (5 * F2_STAGES + F2_TA + a); };
-    auto bar_tempty = [&](int a) { return bars + 8 * (5 * F2_STAGES + F2_TA + 2 + a); };
+    auto bar_ready = [&](int s) { return bars + 8 * (F2_STAGES + s); };         // row updated in place, A operand in tensor memory
+    auto bar_emptyA = [&](int s) { return bars + 8 * (2 * F2_STAGES + s); };    // the stores of the tile have read it
+    auto bar_fullB = [&](int s) { return bars + 8 * (3 * F2_STAGES + s); };     // alpha planes landed
+    auto bar_emptyB = [&](int s) { return bars + 8 * (3 * F2_STAGES + F2_BSTAGES + s); };    // the MMAs of the block have retired
+    auto bar_aempty = [&](int t) { return bars + 8 * (3 * F2_STAGES + 2 * F2_BSTAGES + t); };    // TMEM A slot t read by its MMAs
+    auto bar_tfull = [&](int a) { return bars + 8 * (3 * F2_STAGES + 2 * F2_BSTAGES + F2_TA + a); };
+    auto bar_tempty = [&](int a) { return bars + 8 * (3 * F2_STAGES + 2 * F2_BSTAGES + F2_TA + 2 + a); };
+    auto bar_edge = [&](int e) { return bars + 8 * (3 * F2_STAGES + 2 * F2_BSTAGES + F2_TA + 4 + e); };    // boundary element of block e published
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::OFF_BARS + 8 * L::NUM_BARS);
     float* sinv_ring = reinterpret_cast<float*>(gbase + L::OFF_SINV);
+    float* edge_ring = reinterpret_cast<float*>(gbase + L::OFF_EDGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t TMEM_COLS = 512;
 
     if (warp == 3 && lane == 0) {
-        for (int s = 0; s < F2_STAGES; ++s) {
-            mbar_init(bar_fullA(s), 2); mbar_init(bar_fullB(s), 1); mbar_init(bar_ready(s), 4);
-            mbar_init(bar_emptyA(s), 1); mbar_init(bar_emptyB(s), 1);
-        }
+        for (int s = 0; s < F2_STAGES; ++s) { mbar_init(bar_fullA(s), 2); mbar_init(bar_ready(s), 4); mbar_init(bar_emptyA(s), 1); }
+        for (int s = 0; s < F2_BSTAGES; ++s) { mbar_init(bar_fullB(s), 1); mbar_init(bar_emptyB(s), 1); }
         for (int t = 0; t < F2_TA; ++t) mbar_init(bar_aempty(t), 1);
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
+        for (int e = 0; e < F2_RING; ++e) mbar_init(bar_edge(e), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -164,18 +254,23 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const F2Range R = f2_range(p);
+    F2Work Wk;
+    Wk.init(p);
     const int KB = p.KB;
+    // K block visited at position j of a unit: upwards, except for tiles that move west (dx < 0) — the neighbour a row segment needs
+    // across its block boundary then always belongs to the block visited just before (see the transform warps)
+    auto kb_at = [&](int dx, int kb0, int nblk, int j) { return dx < 0 ? kb0 + nblk - 1 - j : kb0 + j; };
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp < 2) {
             // ===================== producers: gathered rows (64 each), table slices (warp 0), alpha planes (warp 1) =====================
             if (elect_one_sync()) {
+                const uint64_t pol_stream = f2_policy_evict_first(), pol_keep = f2_policy_evict_last();
                 uint32_t it = 0;
-                for (long long g = R.g0; g < R.g1;) {
-                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+                for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
+                    int tile, kb0, nblk;
+                    Wk.unit(u, tile, kb0, nblk);
                     const int a = p.tile_act[tile];
                     const int shift = p.dy[a] * p.Wp;                   // source frame = output frame - dy grid rows (wrap_y: modulo Sp)
                     const bool coef = p.dx[a] != 0;
@@ -185,17 +280,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                     for (int j = 0; j < nblk; ++j, ++it) {
                         const int s = it % F2_STAGES;
                         const uint32_t ph = (it / F2_STAGES) & 1;
-                        const int k0 = (kb0 + j) * F2_BK;
+                        const int k0 = kb_at(p.dx[a], kb0, nblk, j) * F2_BK;
                         int c = k0 - shift;
                         if (c < 0) c += p.Sp;
                         if (c >= p.Sp) c -= p.Sp;
                         const uint32_t st = base + s * L::STAGE;
-                        if (warp == 1) {
-                            mbar_wait(bar_emptyB(s), ph ^ 1);
-                            mbar_expect_tx(bar_fullB(s), 2 * L::B_TILE);
-                            tma_load_2d(st + L::OFF_B1, &tmB1, k0, 0, bar_fullB(s));
-                            tma_load_2d(st + L::OFF_B2, &tmB2, k0, 0, bar_fullB(s));
-                        }
                         mbar_wait(bar_emptyA(s), ph ^ 1);
                         mbar_expect_tx(bar_fullA(s), F2_A_BYTES / 2 + (warp == 0 ? (uint32_t)(p.O + (coef ? 2 : 0)) * F2_BK * 4 : 0u));
                         const uint32_t dst = st + warp * 64 * 128;
@@ -203,80 +292,116 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                         for (int q = 0; q < 16; ++q) {
                             int4 r = __ldg(sl + q);                       // rows of 4 consecutive slots (-1: empty slot, any valid row will do)
                             r.x = max(r.x, 0); r.y = max(r.y, 0); r.z = max(r.z, 0); r.w = max(r.w, 0);
-                            f2_gather4(dst + q * 512, &tmIn, c, r.x, r.y, r.z, r.w, bar_fullA(s));
-                            f2_gather4(dst + F2_BOX + q * 512, &tmIn, c + 32, r.x, r.y, r.z, r.w, bar_fullA(s));
+                            f2_gather4(dst + q * 512, &tmIn, c, r.x, r.y, r.z, r.w, bar_fullA(s), pol_stream);
+                            f2_gather4(dst + F2_BOX + q * 512, &tmIn, c + 32, r.x, r.y, r.z, r.w, bar_fullA(s), pol_stream);
                         }
                         if (warp == 0) {
                             for (int o = 0; o < p.O; ++o)
-                                f2_bulk_1d(st + L::OFF_TAB + o * F2_BK * 4, obs_a + (size_t)o * p.Sp + k0, F2_BK * 4, bar_fullA(s));
+                                f2_bulk_1d(st + L::OFF_TAB + o * F2_BK * 4, obs_a + (size_t)o * p.Sp + k0, F2_BK * 4, bar_fullA(s), pol_keep);
                             if (coef) {
-                                f2_bulk_1d(st + L::OFF_TAB + F2_MAX_O * F2_BK * 4, coef_a + k0, F2_BK * 4, bar_fullA(s));
-                                f2_bulk_1d(st + L::OFF_TAB + (F2_MAX_O + 1) * F2_BK * 4, coef_a + p.Sp + k0, F2_BK * 4, bar_fullA(s));
+                                f2_bulk_1d(st + L::OFF_TAB + F2_MAX_O * F2_BK * 4, coef_a + k0, F2_BK * 4, bar_fullA(s), pol_keep);
+                                f2_bulk_1d(st + L::OFF_TAB + (F2_MAX_O + 1) * F2_BK * 4, coef_a + p.Sp + k0, F2_BK * 4, bar_fullA(s), pol_keep);
                             }
                         }
                     }
-                    g += nblk;
                 }
             }
         } else if (warp == 2) {
-            // ===================== MMA issuer =====================
+            // ===================== MMA issuer (also fetches the alpha planes, one block ahead: they are L2 resident and only the MMAs
+            // read them, so their ring is two deep and independent of how far the row gather runs ahead) =====================
             constexpr uint32_t idesc = make_idesc_f16<BN>();
-            const uint32_t total = (uint32_t)(R.g1 - R.g0);
-            for (uint32_t it = 0; it < total; ++it) {
+            const uint64_t pol_keep = f2_policy_evict_last();
+            // cursor of the block whose planes are fetched next (one block ahead of the MMAs)
+            int pu = blockIdx.x, pj = 0, ptile = 0, pkb0 = 0, pnblk = 0;
+            uint32_t pit = 0;
+            auto cursor_settle = [&]() {          // skip empty units; returns false at the end of this CTA's work
+                while (pu < Wk.num_units) {
+                    Wk.unit(pu, ptile, pkb0, pnblk);
+                    if (pj < pnblk) return true;
+                    pu += gridDim.x; pj = 0;
+                }
+                return false;
+            };
+            auto load_b = [&]() {
+                if (!cursor_settle()) return;
+                const int sb = pit % F2_BSTAGES;
+                const uint32_t bst = base + L::OFF_B + sb * L::BSTAGE;
+                const int k0 = kb_at(p.dx[p.tile_act[ptile]], pkb0, pnblk, pj) * F2_BK;
+                mbar_wait(bar_emptyB(sb), ((pit / F2_BSTAGES) & 1) ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(bar_fullB(sb), 2 * L::B_TILE);
+                    f2_load_2d(bst, &tmB1, k0, 0, bar_fullB(sb), pol_keep);
+                    f2_load_2d(bst + L::B_TILE, &tmB2, k0, 0, bar_fullB(sb), pol_keep);
+                }
+                __syncwarp();
+                ++pit; ++pj;
+            };
+            load_b();
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
+              int tile, kb0, nblk;
+              Wk.unit(u, tile, kb0, nblk);
+              for (int j = 0; j < nblk; ++j, ++it) {
+                load_b();
                 const int s = it % F2_STAGES;
                 const uint32_t ph = (it / F2_STAGES) & 1;
                 const int acc = it & 1;
                 mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+                const int sb = it % F2_BSTAGES;
                 mbar_wait(bar_ready(s), ph);
-                mbar_wait(bar_fullB(s), ph);
+                mbar_wait(bar_fullB(sb), (it / F2_BSTAGES) & 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const int ta = it % F2_TA;
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta, a2 = a1 + 32;
-                    const uint64_t db1 = make_sw128_desc(base + s * L::STAGE + L::OFF_B1), db2 = make_sw128_desc(base + s * L::STAGE + L::OFF_B2);
+                    const uint64_t db1 = make_sw128_desc(base + L::OFF_B + sb * L::BSTAGE), db2 = make_sw128_desc(base + L::OFF_B + sb * L::BSTAGE + L::B_TILE);
                     // cross terms a1.b2 + a2.b1 first, then D = a1.b1 + D * 2^-11 and the remaining main terms
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        tc_mma_f16_ts(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
-                        tc_mma_f16_ts(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
-                    }
+                        for (int kk = 0; kk < F2_BK / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                            tc_mma_f16_ts(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
+                            tc_mma_f16_ts(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                        }
 #pragma unroll
-                    for (int kk = 0; kk < F2_BK / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        if (kk == 0) tc_mma_f16_ts_scale11(d_tmem, a1, db1, idesc);
-                        else tc_mma_f16_ts(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                        for (int kk = 0; kk < F2_BK / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                            if (kk == 0) tc_mma_f16_ts_scale11(d_tmem, a1, db1, idesc);
+                            else tc_mma_f16_ts(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                        }
                     }
-                    tc_commit(bar_emptyB(s));
+                    tc_commit(bar_emptyB(sb));
                     tc_commit(bar_aempty(ta));
                     tc_commit(bar_tfull(acc));
                 }
                 __syncwarp();
+              }
             }
         } else {
             // ===================== store issuer: updated tile -> 128 consecutive rows of b_out =====================
             if (elect_one_sync()) {
                 uint32_t it = 0;
-                for (long long g = R.g0; g < R.g1;) {
-                    const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-                    const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+                for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
+                    int tile, kb0, nblk;
+                    Wk.unit(u, tile, kb0, nblk);
+                    const int sdx = p.dx[p.tile_act[tile]];
                     for (int j = 0; j < nblk; ++j, ++it) {
                         const int s = it % F2_STAGES;
                         mbar_wait(bar_ready(s), (it / F2_STAGES) & 1);
                         const uint32_t src = base + s * L::STAGE;
-                        f2_store_2d(&tmOut, src, (kb0 + j) * F2_BK, tile * BM);
-                        f2_store_2d(&tmOut, src + F2_BOX, (kb0 + j) * F2_BK + 32, tile * BM);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        if (it > 0) {
-                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
+                        if (!(p.dbg & 1)) {
+                            const int k0 = kb_at(sdx, kb0, nblk, j) * F2_BK;
+                            f2_store_2d(&tmOut, src, k0, tile * BM);
+                            f2_store_2d(&tmOut, src + F2_BOX, k0 + 32, tile * BM);
                         }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        // the stage goes back to the producers as soon as the stores have read it (a store read takes a fraction of
+                        // a block period; waiting for the next block's commit first would hold every stage one period longer)
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(bar_emptyA(s));
                     }
-                    g += nblk;
                 }
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                if (it > 0) mbar_arrive(bar_emptyA((it - 1) % F2_STAGES));
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         }
@@ -288,9 +413,9 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
         const int sw = row & 7;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t it = 0;
-        for (long long g = R.g0; g < R.g1;) {
-            const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-            const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+        for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
+            int tile, kb0, nblk;
+            Wk.unit(u, tile, kb0, nblk);
             const int a = p.tile_act[tile];
             const int dx = p.dx[a];
             const int shift = p.dy[a] * p.Wp;
@@ -301,21 +426,27 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
             if (o < 0 || o >= p.O) { o = 0; sc = 0.f; }             // invalid ids fail the row (normaliser 0), like belief_step
             const float* brow = p.b_in + (long long)(src < 0 ? 0 : src) * p.ld;
             float zacc = 0.f;
-            for (int j = 0; j < nblk; ++j, ++it) {
-                if ((int)(it & 1u) != grp) continue;
-                const int kb = kb0 + j;
+            // The neighbour a row segment needs across its block boundary under an x move (the last element of the block before it for
+            // a move east, the first element of the block after it for a move west) belongs to the block this CTA visited just before
+            // (west tiles walk K downwards), which the OTHER transform group owns: every group publishes the raw boundary element of its
+            // block in shared memory before it rewrites the tile in place.  (Fetching it from global memory instead — one scattered
+            // 4-byte load per row and block — cost 0.7-0.9 ms per step: the streamed rows are evict-first in L2.)  Only the first
+            // block of a unit that starts inside a tile (K split of the last wave) reads its neighbour from global memory.
+            const int j_first = (int)((grp - (int)(it & 1u)) & 1);
+            const uint32_t it_seg = it;
+            for (int j = j_first; j < nblk; j += 2) {
+                it = it_seg + j;
+                const int kb = kb_at(dx, kb0, nblk, j);
                 const int s = it % F2_STAGES;
                 const uint32_t ph = (it / F2_STAGES) & 1;
                 const int ta = it % F2_TA;
-                // the neighbour across the block boundary of an x move comes straight from HBM / L2 (one float per row and block),
-                // requested before the waits so that its latency hides behind them
                 float halo = 0.f;
-                if (dx != 0) {
+                if (dx != 0 && j == 0) {
                     int c = kb * F2_BK - shift;
                     if (c < 0) c += p.Sp;
                     if (c >= p.Sp) c -= p.Sp;
                     int hc = dx > 0 ? c - 1 : c + F2_BK;
-                    hc = hc < 0 ? 0 : (hc >= p.Sp ? p.Sp - 1 : hc);   // out of range only where the mask is 0: any finite value will do
+                    hc = hc < 0 ? 0 : (hc >= p.Sp ? p.Sp - 1 : hc);       // out of range only where the mask is 0: any finite value will do
                     halo = ld_stream1(brow + hc);
                 }
                 mbar_wait(bar_fullA(s), ph);
@@ -323,51 +454,43 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                 tc_fence_after();
                 uint8_t* stage = gbase + s * L::STAGE;
                 uint8_t* rowp = stage + row * 128;
+                if (dx != 0) {
+                    // raw boundary element of this block: element 63 (move east) / element 0 (move west) of the row segment
+                    const float mine = dx > 0 ? *reinterpret_cast<const float*>(rowp + F2_BOX + ((7 ^ sw) << 4) + 12)
+                                              : *reinterpret_cast<const float*>(rowp + ((0 ^ sw) << 4));
+                    edge_ring[(it % F2_RING) * BM + row] = mine;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_edge(it % F2_RING));       // every block arrives (the phase of the barrier counts blocks)
+                if (dx != 0) {
+                    if (j > 0) {
+                        const uint32_t ip = it - 1;
+                        mbar_wait(bar_edge(ip % F2_RING), (ip / F2_RING) & 1);
+                        halo = edge_ring[(ip % F2_RING) * BM + row];
+                    }
+                }
                 const float* tab = reinterpret_cast<const float*>(stage + L::OFF_TAB);
                 const float* lik = tab + o * F2_BK;
                 const float* cA = tab + F2_MAX_O * F2_BK;
                 const float* cB = cA + F2_BK;
                 float bp[F2_BK];                                    // the updated row segment
                 float mx = 0.f;
-                if (dx == 0) {
+                if (p.dbg & 8) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        float4* q = reinterpret_cast<float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4));
-                        const float4 v = *q;
-                        const float4 l = *reinterpret_cast<const float4*>(lik + 4 * c);
-                        float4 r;
-                        r.x = v.x * sc * l.x; r.y = v.y * sc * l.y; r.z = v.z * sc * l.z; r.w = v.w * sc * l.w;
-                        *q = r;
-                        zacc += (r.x + r.y) + (r.z + r.w);
-                        mx = fmaxf(fmaxf(mx, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
-                        bp[4 * c] = r.x; bp[4 * c + 1] = r.y; bp[4 * c + 2] = r.z; bp[4 * c + 3] = r.w;
-                    }
+                    for (int k = 0; k < F2_BK; ++k) bp[k] = 0.f;
+                } else if (dx == 0) {
+                    f2_update<0, false>(rowp, sw, lik, cA, cB, sc, halo, bp, zacc, mx);
                 } else {
-                    float v[F2_BK];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float4 t = *reinterpret_cast<const float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4));
-                        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float4 l = *reinterpret_cast<const float4*>(lik + 4 * c);
-                        const float4 ma = *reinterpret_cast<const float4*>(cA + 4 * c);
-                        const float4 mb = *reinterpret_cast<const float4*>(cB + 4 * c);
-                        const float la[4] = {l.x, l.y, l.z, l.w}, ca[4] = {ma.x, ma.y, ma.z, ma.w}, cb[4] = {mb.x, mb.y, mb.z, mb.w};
-                        float r[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = 4 * c + e;
-                            // value arriving from one cell back along the move (k - dx), from the halo across the block boundary
-                            const float nb = dx > 0 ? (k == 0 ? halo : v[k > 0 ? k - 1 : 0]) : (k == F2_BK - 1 ? halo : v[k < F2_BK - 1 ? k + 1 : k]);
-                            const float w = fmaf(ca[e], nb, cb[e] * v[k]);          // masks are 0 / 1: exact, one rounding for the merged cell
-                            r[e] = w * sc * la[e];
-                        }
-                        *reinterpret_cast<float4*>(rowp + (c >> 3) * F2_BOX + (((c & 7) ^ sw) << 4)) = make_float4(r[0], r[1], r[2], r[3]);
-                        zacc += (r[0] + r[1]) + (r[2] + r[3]);
-                        mx = fmaxf(fmaxf(mx, fmaxf(r[0], r[1])), fmaxf(r[2], r[3]));
-                        bp[4 * c] = r[0]; bp[4 * c + 1] = r[1]; bp[4 * c + 2] = r[2]; bp[4 * c + 3] = r[3];
+                    // a block is 64 consecutive columns of one grid row (Wp % 64 == 0): only the first block of a row (column 0) and the
+                    // one that holds the clipped edge / the padding need the masks
+                    const int x0 = (kb * F2_BK) % p.Wp;
+                    const bool masked = x0 == 0 || x0 + F2_BK - 1 > p.W - 2;
+                    if (dx > 0) {
+                        if (masked) f2_update<1, true>(rowp, sw, lik, cA, cB, sc, halo, bp, zacc, mx);
+                        else        f2_update<1, false>(rowp, sw, lik, cA, cB, sc, halo, bp, zacc, mx);
+                    } else {
+                        if (masked) f2_update<-1, true>(rowp, sw, lik, cA, cB, sc, halo, bp, zacc, mx);
+                        else        f2_update<-1, false>(rowp, sw, lik, cA, cB, sc, halo, bp, zacc, mx);
                     }
                 }
                 // block scale: the power of two that brings the block's maximum into [2^13, 2^14)
@@ -376,6 +499,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                 const float scl = __uint_as_float(es << 23);
                 sinv_ring[(it % F2_RING) * BM + row] = __uint_as_float((254u - es) << 23);
                 const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * ta;
+                if (!(p.dbg & 4))
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t h[16], l[16];
@@ -401,9 +525,9 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready(s));
             }
+            it = it_seg + nblk;
             // normaliser share of this segment (both groups write theirs; the finishing kernel adds them in a fixed order)
-            p.ws_z[((long long)(tile + blockIdx.x) * 2 + grp) * BM + row] = zacc;
-            g += nblk;
+            p.ws_z[((long long)u * 2 + grp) * BM + row] = zacc;
         }
     } else if (warp < 16) {
         // ===================== epilogue: block accumulators -> FP32 register sums -> partial sums of the segment =====================
@@ -411,15 +535,17 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t it = 0;
-        for (long long g = R.g0; g < R.g1;) {
-            const int tile = (int)(g / KB), kb0 = (int)(g - (long long)tile * KB);
-            const int nblk = (int)((R.g1 - g < KB - kb0) ? (R.g1 - g) : (KB - kb0));
+        for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
+            int tile, kb0, nblk;
+            Wk.unit(u, tile, kb0, nblk);
             float sum[BN];
 #pragma unroll
             for (int j = 0; j < BN; ++j) sum[j] = 0.f;
             for (int j = 0; j < nblk; ++j, ++it) {
                 const int acc = it & 1;
-                mbar_wait(bar_ready(it % F2_STAGES), (it / F2_STAGES) & 1);       // the block's A scales were written before this
+                // (no wait on bar_ready here: the epilogue may run more than one phase of that barrier behind the transform, and a parity
+                // wait that is lapped never returns.  The block's A scale was written before the transform arrived on bar_ready; the MMA
+                // thread acquired that barrier before it issued the MMAs whose commit this wait acquires: visible by causality.)
                 mbar_wait(bar_tfull(acc), (it >> 1) & 1);
                 tc_fence_after();
                 const float sinv = sinv_ring[(it % F2_RING) * BM + row];
@@ -434,12 +560,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty(acc));
             }
-            float* wsrow = p.ws_sum + ((long long)(tile + blockIdx.x) * BM + row) * BN;
+            float* wsrow = p.ws_sum + ((long long)u * BM + row) * BN;
 #pragma unroll
             for (int j = 0; j < BN; j += 4)
                 *reinterpret_cast<float4*>(wsrow + j) = make_float4(sum[j] * __ldg(p.binv + j), sum[j + 1] * __ldg(p.binv + j + 1),
                                                                     sum[j + 2] * __ldg(p.binv + j + 2), sum[j + 3] * __ldg(p.binv + j + 3));
-            g += nblk;
         }
     }
 
@@ -580,12 +705,16 @@ __global__ void __launch_bounds__(128) fused2_finish_kernel(int BN, int G, int K
     const long long slot = (long long)tile * BM + l;
     const int src = slot_src[slot];
     if (src < 0) { scale_out[slot] = 0.f; return; }
-    const long long total = (long long)nt * KB;
-    const long long per = (total + grid_main - 1) / grid_main;
-    const int c_first = (int)(((long long)tile * KB) / per), c_last = (int)((((long long)tile + 1) * KB - 1) / per);
+    // the units that hold this tile's partial sums (same arithmetic as F2Work)
+    const int full_units = (nt / grid_main) * grid_main;
+    const int tail = nt - full_units;
+    int split = tail ? (grid_main / tail < 8 ? grid_main / tail : 8) : 1;
+    if (split < 1) split = 1;
+    const int u0 = tile < full_units ? tile : full_units + (tile - full_units) * split;
+    const int nu = tile < full_units ? 1 : split;
     float z = 0.f;
-    for (int c = c_first; c <= c_last; ++c) {
-        const float* zs = ws_z + (long long)(tile + c) * 2 * BM;
+    for (int c = 0; c < nu; ++c) {
+        const float* zs = ws_z + (long long)(u0 + c) * 2 * BM;
         z += zs[l];
         z += zs[BM + l];
     }
@@ -593,8 +722,8 @@ __global__ void __launch_bounds__(128) fused2_finish_kernel(int BN, int G, int K
     int best_idx = 0;
     for (int j0 = 0; j0 < G; j0 += 4) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = c_first; c <= c_last; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(ws_sum + ((long long)(tile + c) * BM + l) * BN + j0);
+        for (int c = 0; c < nu; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(ws_sum + ((long long)(u0 + c) * BM + l) * BN + j0);
             x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
         }
         const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -717,7 +846,8 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
 
     F2Params p;
     memset(&p, 0, sizeof(p));
-    p.b_in = b_in; p.ld = ld; p.KB = g.Sp / F2_BK; p.Sp = g.Sp; p.Wp = g.Wp;
+    p.b_in = b_in; p.ld = ld; p.KB = g.Sp / F2_BK; p.Sp = g.Sp; p.Wp = g.Wp; p.W = g.W;
+    { const char* e = getenv("OLFNAV_F2_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.n_tiles_max = n_tiles_max; p.n_tiles_dev = n_tiles_dev; p.tile_act = tile_act; p.slot_src = slot_src; p.slot_obs = slot_obs;
     p.scale_in = scale_in; p.obs_tab = m->obs; p.coef = m->coef; p.A = g.A; p.O = g.O; p.obs_per_action = g.obs_per_action;
     for (int k = 0; k < g.A; ++k) { p.dy[k] = g.moves[k][0]; p.dx[k] = g.moves[k][1]; }

@@ -399,9 +399,45 @@ class BeliefSet:
         s = torch.cat([self._scale[:self._n], other._scale[:other._n]], dim=0)
         return BeliefSet(self.model, _buffers=(b, s, self._n + other._n), device=self.device)
 
-    def generate_all_successors(self, *args, **kwargs):
-        raise NotImplementedError('successor beliefs are never materialised on the B200 path: use '
-                                  'Infotaxis_Agent.choose_action / olfnav_infotaxis_choose (fused expected-entropy kernel)')
+    def generate_all_successors(self, use_reachability: bool = True, raise_on_impossible_belief: bool = False,
+                                return_provenance: bool = False, max_bytes: int = 8 << 30):
+        '''
+        Every successor b_{a,o} of every belief of the set (toolkit surface used at agents/infotaxis_agent.py:260-262): ONE
+        olfnav_belief_step launch over the (belief, action, observation) triples, impossible successors (normaliser 0) dropped.
+        Returns the BeliefSet (rows ordered by belief, then action, then observation) and, with return_provenance, the (k, 3) int
+        array of (source belief, action, observation) of the rows kept.
+        This MATERIALISES n * A * O rows of S floats and exists for API fidelity on small sets (the reference's own
+        Infotaxis_Agent can then run on this toolkit surface); Infotaxis_Agent.choose_action of this package never does
+        (olfnav_infotaxis_choose).  Sets whose successors exceed `max_bytes` are refused.
+        '''
+        m = self.model
+        n, A, O = self._n, m.action_count, m.observation_count
+        total = n * A * O
+        need = total * m.padded_states * 4
+        if need > max_bytes:
+            raise MemoryError(f'generate_all_successors would materialise {total} rows ({need / 2**30:.1f} GiB): use '
+                              'Infotaxis_Agent.choose_action / olfnav_infotaxis_choose, which never builds them')
+        dev = self._b.device
+        idx = torch.arange(total, device=dev)
+        rows = (idx // (A * O)).to(torch.int32).contiguous()
+        act = ((idx // O) % A).to(torch.int32).contiguous()
+        obs = (idx % O).to(torch.int32).contiguous()
+        out_b = torch.empty((max(total, 1), self._b.shape[1]), dtype=torch.float32, device=dev)
+        out_s = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        ok = torch.zeros(max(total, 1), dtype=torch.uint8, device=dev)
+        if total:
+            with torch.cuda.device(self.device):
+                check(lib.olfnav_belief_step(m.handle(self.device), ptr(self._b), ptr(out_b), self.ld, total, ptr(act), ptr(obs), ptr(rows), None,
+                                             ptr(self._scale), ptr(out_s), ptr(ok), stream()))
+        keep = torch.nonzero(ok[:total].bool()).flatten()
+        if raise_on_impossible_belief and int(keep.numel()) < total:
+            raise ValueError('Impossible belief update (the observation has probability 0 under the belief and action)')
+        new = BeliefSet(m, _buffers=(out_b[keep].contiguous() if int(keep.numel()) else out_b[:1], out_s[keep].contiguous() if int(keep.numel()) else out_s[:1],
+                                     int(keep.numel())), device=self.device)
+        if return_provenance:
+            prov = torch.stack([rows.long()[keep], act.long()[keep], obs.long()[keep]], dim=1).cpu().numpy()
+            return new, prov
+        return new
 
 
 class Belief:

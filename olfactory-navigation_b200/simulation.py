@@ -641,6 +641,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             nbytes = int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size()
             v[name] = buf[o:o + nbytes].view(dt).view(shape)
             o += nbytes
+        v['_raw'] = buf
         return v
     rec_bytes = 22 * cap
     rec_dev = [torch.empty(rec_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -651,12 +652,16 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     pending = []
 
     def flush(upto: int) -> None:
+        # One copy of the step's 22-byte records out of the pinned staging set (it is reused two steps later); the history keeps
+        # typed views of that copy (int32 ids / positions, uint8 flags) and widens them lazily when a table is asked for.  Five
+        # astype / copy passes over 100 000 rows per step and rank used to sit here, on host cores that 8 ranks share.
         while len(pending) > upto:
             ev, h, m_rec = pending.pop(0)
             ev.synchronize()
-            hist.add_step(actions=h['act'].numpy()[:m_rec].astype(np.int64), next_positions=h['pos'].numpy()[:m_rec].astype(np.int64),
-                          observations=h['odor'].numpy()[:m_rec].copy(), reached_source=h['reached'].numpy()[:m_rec].astype(bool),
-                          interupt=h['term'].numpy()[:m_rec].astype(bool), action_is_id=True)
+            own = record_views(h['_raw'].clone())
+            hist.add_step(actions=own['act'].numpy()[:m_rec], next_positions=own['pos'].numpy()[:m_rec], observations=own['odor'].numpy()[:m_rec],
+                          reached_source=own['reached'].numpy()[:m_rec].view(np.bool_), interupt=own['term'].numpy()[:m_rec].view(np.bool_),
+                          action_is_id=True)
 
     def run_policy(b, scale, rows: int, act_out) -> None:
         'argmax_g b.alpha_g -> action id (agents/pbvi_agent.py:741) or the infotaxis choice (agents/infotaxis_agent.py:244-301).'
@@ -671,13 +676,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     brow = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
     brow_valid = False                 # False: agent i's belief is row i (start of the run, or after an explicit compaction)
 
-    def rows_to_slot_order(m: int) -> None:
-        'Gather the m live belief rows back into agent order (row i = agent i): before a compaction by mask and at the end of the run.'
-        src, dst = agent._cur, 1 - agent._cur
-        with torch.cuda.device(device):
-            check(lib.olfnav_copy_rows(ptr(agent._bufs[src]), ptr(agent._bufs[dst]), agent._bufs[src].stride(0), model.padded_states,
-                                       ptr(brow[cur]), ptr(agent._scales[src]), ptr(agent._scales[dst]), m, stream()))
-        agent._cur = dst
+    act_next_buf = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
+
     n_live, cur = n, 0
     have_act = False                   # the next step's actions were computed ahead of time (see the end of the loop body)
     iterator = range(horizon)
@@ -713,14 +713,18 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
         args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
         args.counts = counts.data_ptr()
-        # (also on the last step of the horizon: the policy rides along for free and the rows stay grouped until the end of the run)
-        args.act_next = recs[(i + 1) & 1]['act'].data_ptr() if fused else None
         if fused:
+            # The update of this step also delivers the NEXT step's actions (also on the last step of the horizon: the policy rides
+            # along for free).  They go to a buffer of their own and move into the record set at the start of the step that plays
+            # them: the record set of step i + 1 is still on its way to the host while step i runs.
+            if have_act:
+                r['act'][:n_live].copy_(act_next_buf[i & 1][:n_live], non_blocking=True)
+            args.act_next = act_next_buf[(i + 1) & 1].data_ptr()
             args.brow_in = brow[cur].data_ptr() if brow_valid else None
             args.brow_out = brow[1 - cur].data_ptr()
             args.belief_rows = int(b_cur.shape[0])
-        if fused and rec_free[(i + 1) & 1] is not None:
-            main.wait_event(rec_free[(i + 1) & 1])             # the next record set receives its actions during this step
+        else:
+            args.act_next = None
         if timing is not None:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             for e in evs:
@@ -741,7 +745,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         have_act = i + 1 < horizon
         if have_act:
             nxt = recs[(i + 1) & 1]
-            if rec_free[(i + 1) & 1] is not None:
+            if not fused and rec_free[(i + 1) & 1] is not None:
                 main.wait_event(rec_free[(i + 1) & 1])
             if timing is not None:
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -773,8 +777,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         brow_valid = fused
         if n_fail or n_end:
             # rare: some survivors must still go (impossible update / end of the recording): explicit compaction
-            if fused and brow_valid and m:
-                rows_to_slot_order(m)
+            if fused and brow_valid:
+                agent._row_map = brow[cur]
+                agent._rows_to_agent_order()
                 brow_valid = False
             keep = ~term_c[:m].bool()
             rows = torch.nonzero(keep).flatten()
@@ -783,7 +788,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 pos[1 - cur][:k] = pos[cur][:m][rows]
                 ts[1 - cur][:k] = ts[cur][:m][rows]
                 if have_act:
-                    nxt['act'][:k] = nxt['act'][:m][rows]
+                    nact = act_next_buf[(i + 1) & 1] if fused else nxt['act']
+                    nact[:k] = nact[:m][rows]
             cur = 1 - cur
             agent.kill_device(~keep)
             m = k
@@ -795,7 +801,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     if n_live == 0:
         agent._bufs = None
     elif fused and brow_valid:
-        rows_to_slot_order(n_live)         # the agent's state is left in agent order, like after the two-kernel loop
+        agent._row_map = brow[cur][:n_live].clone()      # rows still grouped by action: put back in agent order on first use
     return hist
 
 

@@ -36,6 +36,31 @@ for exchange in ('indices', 'alphas'):
     assert torch.equal(sh_a, full_a), f'sharded backup ({exchange}): actions differ'
     assert torch.equal(sh_alpha, full_alpha), f'sharded backup ({exchange}): alpha vectors differ'
 
+# ---- training through the Agent API: train() under the process group shards every backup; must equal the unsharded training ----
+os.environ['OLFNAV_SHARDED_TRAIN'] = '0'
+ref_agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+ref_agent.train(expansions=8, print_progress=False, print_stats=False)
+os.environ['OLFNAV_SHARDED_TRAIN'] = '1'
+sh_agent = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=onb.synthetic.SEED)
+sh_agent.train(expansions=8, print_progress=False, print_stats=False)
+assert np.array_equal(sh_agent.value_function.actions, ref_agent.value_function.actions), 'sharded train(): actions differ'
+assert torch.equal(sh_agent.value_function.device_alphas(), ref_agent.value_function.device_alphas()), 'sharded train(): alpha vectors differ'
+for cls in (onb.agents.PBVI_SSRA_Agent, onb.agents.PBVI_GER_Agent):
+    os.environ['OLFNAV_SHARDED_TRAIN'] = '0'
+    r = cls(env, thresholds=c['thresholds'], rng=3)
+    r.train(expansions=4, max_belief_growth=6, print_progress=False, print_stats=False)
+    os.environ['OLFNAV_SHARDED_TRAIN'] = '1'
+    t = cls(env, thresholds=c['thresholds'], rng=3)
+    t.train(expansions=4, max_belief_growth=6, print_progress=False, print_stats=False)
+    assert torch.equal(t.value_function.device_alphas(), r.value_function.device_alphas()), f'sharded train() of {cls.__name__}: alpha vectors differ'
+# different seeds on the ranks are refused
+try:
+    bad = onb.agents.FSVI_Agent(env, thresholds=c['thresholds'], rng=100 + rank)
+    bad.train(expansions=1, print_progress=False, print_stats=False)
+    raise SystemExit('sharded train() accepted rank-dependent seeds')
+except RuntimeError:
+    pass
+
 # ---- simulation ----
 n = 203
 starts = env.random_start_points(n, np.random.default_rng(11))
@@ -48,6 +73,6 @@ if rank == 0:
     assert np.array_equal(sharded.reached_source, single.reached_source)
     assert np.array_equal(np.array(sharded.positions), np.array(single.positions))
     assert np.array_equal(np.array(sharded.actions), np.array(single.actions))
-    print(f'multi-GPU check OK on {ws} ranks: backup ({B} points, G={alphas.shape[0]}) and run_test ({n} agents, {int(single.reached_source.sum())} reached) identical to 1 GPU')
+    print(f'multi-GPU check OK on {ws} ranks: backup ({B} points, G={alphas.shape[0]}) and run_test ({n} agents, {int(single.reached_source.sum())} reached) identical to 1 GPU; FSVI / SSRA / GER train() sharded == unsharded')
 dist.barrier()
 dist.destroy_process_group()

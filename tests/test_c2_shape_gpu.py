@@ -167,11 +167,14 @@ def test_backup_c2_vs_oracle(f16, monkeypatch):
 
 def test_fsvi_training_c2_strict_and_the_75_vs_74_ties():
     '''
-    (1) Same MDP policy on both sides (the oracle's VI solution) -> the device FSVI must reproduce the oracle FSVI under the strict
-        solver contract at the benchmark shape: same belief counts, same points, same number of alpha vectors, same values.
-    (2) With each side's OWN value iteration the two trainings differ (device 75 alpha vectors, oracle 74 at expansions = 10): the MDP
-        policies must differ only at states where the two best actions are tied in float64 (both solutions, relative 1e-9) — a
-        documented tie, not a divergence of the solver.
+    FSVI at the benchmark shape, device solver against oracle solver (the bench's training call: expansions = 10).
+    (0) Value iteration: 918 sweeps on both sides, Q within 1e-6; the two MDP policies differ only at states where the best two
+        actions are tied in float64 (wrap_vertical with the source on the middle row makes north and south equivalent).
+    (1) With one MDP policy on both sides the two trainings select the same belief points and hold the strict solver contract (same
+        number of alpha vectors, same value function) expansion by expansion — until a backup meets an EXACT tie: a belief point
+        whose two best actions have the same float64 value (relative gap below 1e-9; measured: 1.9e-16 between "south" and "west" at
+        expansion 3).  np.argmax and the device then keep different (equally good) vectors, which is how the default trainings come to
+        75 and 74 vectors.  The test finds that backup and proves the tie; a divergence that is not an exact tie fails it.
     '''
     import olfactory_navigation_b200 as onb
     om = _oracle()['model']
@@ -183,29 +186,55 @@ def test_fsvi_training_c2_strict_and_the_75_vs_74_ties():
     Qo, Qd = vi_o.alpha_vector_array, vi_d.alpha_vector_array
     assert len(hist_o.value_function_changes) == len(hist_d.value_function_changes) == 918
     np.testing.assert_allclose(Qd, Qo, rtol=1e-6)
-    # (2) the policies differ only at exact ties
     po, pd = np.argmax(Qo, axis=0), np.argmax(Qd, axis=0)
     diff = np.flatnonzero(po != pd)
     for Q in (Qo, Qd):
         gap = np.abs(Q[po[diff], diff] - Q[pd[diff], diff])
         assert np.all(gap <= 1e-9 * np.abs(Q[po[diff], diff])), 'MDP policies differ at a state that is not a float64 tie'
-    # tied states exist at this shape (wrap_vertical with the source on the middle row makes north and south equivalent far away),
-    # which is how the two default trainings come to 75 and 74 vectors
-    top2 = np.sort(Qo, axis=0)[-2:]
-    assert np.sum((top2[1] - top2[0]) <= 1e-9 * np.abs(top2[1])) > 0
-    # (1) strict contract under one policy
-    kw = dict(expansions=10, gamma=0.99, eps=1e-6, print_progress=False, print_stats=False)
-    ref_vf, ref_hist = tk.solvers.FSVI.solve(om, rng=np.random.default_rng(onb.synthetic.SEED), mdp_policy=vi_o, **kw)[:2]
+
     shared = onb.ValueFunction(m, Qo, np.arange(4))
-    got_vf, got_hist = onb.solvers.FSVI.solve(m, rng=np.random.default_rng(onb.synthetic.SEED), mdp_policy=shared, **kw)[:2]
-    assert got_hist.beliefs_counts == ref_hist.beliefs_counts
-    rb = ref_hist.final_belief_set.belief_array
-    np.testing.assert_allclose(got_hist.final_belief_set.belief_array, rb, rtol=2e-5, atol=1e-12)
-    assert len(got_vf) == len(ref_vf)
-    rng = np.random.default_rng(3)
-    pts = -np.log(1.0 - rng.random((32, om.state_count)))
-    pts = np.vstack([rb, pts / pts.sum(1, keepdims=True)])
-    vr = np.max(pts @ ref_vf.alpha_vector_array.T, axis=1)
-    vg = np.max(pts @ got_vf.alpha_vector_array.T, axis=1)
-    np.testing.assert_allclose(vg, vr, rtol=1e-5, atol=1e-9)
-    assert np.array_equal(got_vf.actions, ref_vf.actions)
+    seed = onb.synthetic.SEED
+    prev = None
+    tie_found = False
+    for E in range(1, 11):
+        kw = dict(expansions=E, gamma=0.99, eps=1e-6, print_progress=False, print_stats=False)
+        ref_vf, ref_hist = tk.solvers.FSVI.solve(om, rng=np.random.default_rng(seed), mdp_policy=vi_o, **kw)[:2]
+        got_vf, got_hist = onb.solvers.FSVI.solve(m, rng=np.random.default_rng(seed), mdp_policy=shared, **kw)[:2]
+        # the belief points never depend on the value function in FSVI: identical all the way
+        assert got_hist.beliefs_counts == ref_hist.beliefs_counts
+        rb = ref_hist.final_belief_set.belief_array
+        np.testing.assert_allclose(got_hist.final_belief_set.belief_array, rb, rtol=2e-5, atol=1e-12)
+        if len(got_vf) == len(ref_vf):
+            # strict contract: same value function as a function, same actions
+            rng = np.random.default_rng(3)
+            pts = -np.log(1.0 - rng.random((32, om.state_count)))
+            pts = np.vstack([rb, pts / pts.sum(1, keepdims=True)])
+            np.testing.assert_allclose(np.max(pts @ got_vf.alpha_vector_array.T, axis=1), np.max(pts @ ref_vf.alpha_vector_array.T, axis=1),
+                                       rtol=1e-5, atol=1e-9)
+            assert np.array_equal(np.sort(got_vf.actions), np.sort(ref_vf.actions))
+            prev = (ref_vf, ref_hist)
+            continue
+        # first expansion whose backup differs: redo it in float64 from the (common) state before it
+        p_vf = prev[0] if prev else tk.ValueFunction(om, om.expected_rewards_table.T.copy(), om.actions)
+        nb = rb[(prev[1].beliefs_counts[-1] if prev else 1):]
+        _, det = tk.solvers.backup(om, tk.BeliefSet(om, nb), p_vf, gamma=0.99, append=True, belief_dominance_prune=True, return_details=True)
+        vf_prev = onb.ValueFunction(m, p_vf.alpha_vector_array, p_vf.actions)
+        _, best_a, best_v, best_g = onb.solvers.backup_device(m, onb.BeliefSet(m, nb.astype(np.float32).astype(np.float64)), vf_prev.device_alphas(0), 0.99, 0)
+        best_a, best_g = best_a.cpu().numpy(), best_g.cpu().numpy()
+        np.testing.assert_allclose(best_v.cpu().numpy(), det['new_value'], rtol=1e-5)
+        differing = np.flatnonzero(best_a != det['best_a'])
+        assert len(differing) >= 1, 'the alpha counts differ although every belief point chose the same action'
+        for b in differing:
+            q = det['q'][b]
+            assert abs(q[det['best_a'][b]] - q[best_a[b]]) <= 1e-9 * abs(q[det['best_a'][b]]), \
+                f'expansion {E}, belief point {b}: actions {det["best_a"][b]} / {best_a[b]} differ without a float64 tie (q = {q})'
+        same = best_a == det['best_a']
+        sc = np.einsum('bs,aogs->baog', nb, tk.solvers.gamma_a_o(om, p_vf.alpha_vector_array, 0.99))
+        srt = np.sort(sc, axis=3)
+        g_clear = (srt[..., -1] - srt[..., -2]) > 1e-5 * (np.abs(det['new_value'])[:, None, None] + 1e-30)
+        assert np.array_equal(best_g[g_clear], det['best_g'][g_clear])
+        tie_found = True
+        break
+    # at this shape, seed and training call the tie is met (the 75-vs-74 of the bench); if a future change removes it, the strict
+    # contract above has held for all ten expansions instead
+    assert tie_found or len(got_vf) == len(ref_vf)

@@ -198,3 +198,29 @@ def test_in_place_rotated_traversal_tall_grid(boundary, rot_inplace, monkeypatch
         ref = tk.BeliefSet(om, B[:40]).update(acts[:40], obs[:40], raise_on_impossible_belief=False)
         got = onb.BeliefSet(m, _buffers=(ip_b, ip_s, n), device=0).belief_array[:40]
         np.testing.assert_allclose(got, ref.belief_array, rtol=1e-5, atol=1e-30)
+
+
+def test_generate_all_successors_matches_the_oracle():
+    '''
+    BeliefSet.generate_all_successors (toolkit surface of the reference's own Infotaxis_Agent, agents/infotaxis_agent.py:260-262):
+    same rows, same order, same provenance as the oracle; refused (MemoryError) when the successors would not fit the budget.
+    '''
+    import olfactory_navigation_b200 as onb
+    from oracle import refloader
+    refloader.install_oracle_toolkit()
+    import pomdp_toolkit as tk
+    _, agent = make('T1')
+    m, om = agent.model, oracle_model(agent.model)
+    rng = np.random.default_rng(4)
+    d = -np.log(1.0 - rng.random((7, m.state_count)))
+    B = (d / d.sum(1, keepdims=True)).astype(np.float32).astype(np.float64)
+    B[0] = 0
+    B[0, 3] = 1.0                                          # a point mass: most successors are impossible
+    got, prov = onb.BeliefSet(m, B).generate_all_successors(return_provenance=True)
+    ref, rprov = tk.BeliefSet(om, B).generate_all_successors(raise_on_impossible_belief=False, return_provenance=True)
+    assert np.array_equal(prov, rprov) and len(got) == len(ref) < 7 * m.action_count * m.observation_count
+    np.testing.assert_allclose(got.belief_array, ref.belief_array, rtol=1e-5, atol=1e-30)
+    with pytest.raises(MemoryError):
+        onb.BeliefSet(m, B).generate_all_successors(max_bytes=1024)
+    with pytest.raises(ValueError):
+        onb.BeliefSet(m, B).generate_all_successors(raise_on_impossible_belief=True)

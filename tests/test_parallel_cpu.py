@@ -50,6 +50,13 @@ def _worker(rank: int, ws: int, port: int, q):
         # empty contribution from one rank
         e, ea = parallel.all_gather_alphas(rows[:0] if rank == 0 else rows, acts[:0] if rank == 0 else acts)
         assert e.shape[0] == sum((r + 2) for r in range(1, ws))
+        # sharded training refuses generators that differ between the ranks (the expand step is replicated on the host)
+        parallel.assert_same_rng(np.random.default_rng(5), 'cpu')
+        try:
+            parallel.assert_same_rng(np.random.default_rng(5 + rank), 'cpu')
+            raise AssertionError('different generators were accepted')
+        except RuntimeError:
+            pass
         # history gather + concatenation in rank order (the pickled histories travel through gather_object)
         c = onb.synthetic.config('T0')
         env = onb.Environment(**c['env_kwargs'])
