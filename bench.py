@@ -320,7 +320,7 @@ def run_ours(args) -> None:
             ev_ms.append(evs[5].elapsed_time(evs[6]) if len(evs) > 6 else evs[0].elapsed_time(evs[1]))
             bs_ms.append(evs[2].elapsed_time(evs[3]))
             bs_bytes.append(8.0 * S * counts)            # survivors actually updated by the kernel
-        return hist._agent_steps, bs_ms, bs_bytes, ev_ms, loop_start
+        return hist._agent_steps, bs_ms, bs_bytes, ev_ms, loop_start, getattr(hist, '_step_mode', 'two_kernel')
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -339,7 +339,8 @@ def run_ours(args) -> None:
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     torch.cuda.nvtx.range_push('timed')
-    agent_steps, bs_ms, bs_bytes, ev_ms, loop_start = device_loop(args.steps, True)
+    agent_steps, bs_ms, bs_bytes, ev_ms, loop_start, step_mode = device_loop(args.steps, True)
+    fused = step_mode == 'one_pass'
     torch.cuda.nvtx.range_pop()
     t1.record()
     barrier()
@@ -400,7 +401,7 @@ def run_ours(args) -> None:
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'{args.config} {label}: ' + WORKLOADS[CONFIG],
-                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': evaluate_path, 'one_pass_step': bool(fused),
+                       'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': evaluate_path, 'one_pass_step': bool(fused), 'step_mode': step_mode,
                        'sharding': 'agents split across ranks, no data-path collective',
                        'layout': 'grid rows padded to %d floats (%d padded states for %d states)' % (model.padded_width, Sp, S),
                        'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * Sp * 4 / 1e9)},

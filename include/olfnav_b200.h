@@ -196,6 +196,15 @@ int olfnav_backup_select(const olfnav_model* m, const float* b, int64_t ld, int6
 int olfnav_backup_assemble(const olfnav_model* m, const float* gamma_ao, int64_t ld_gamma, int G,
                            const int32_t* best_g, const int32_t* best_a, int64_t n_beliefs,
                            float* alpha_new, int64_t ld_new, void* stream);
+/* The same backup without Gamma in memory (grid models, tensor path): the selection builds the FP16 operand planes of Gamma straight
+ * from the alpha vectors, the assembly recomputes the selected Gamma rows from them (bit-identical vectors to the three calls above;
+ * at G = 512 the FP32 Gamma is 783 MB).  alpha [dev] G x ld_alpha in the padded layout. */
+int olfnav_backup_select_alphas(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
+                                const float* alpha, int64_t ld_alpha, int G, float discount,
+                                int32_t* best_g, int32_t* best_a, float* best_value, void* stream);
+int olfnav_backup_assemble_alphas(const olfnav_model* m, const float* alpha, int64_t ld_alpha, int G, float discount,
+                                  const int32_t* best_g, const int32_t* best_a, int64_t n, float* alpha_new, int64_t ld_new,
+                                  void* stream);
 
 /* Row-pair reductions used by the belief-point selection heuristics and the pruning of solvers.*.solve
  * (agents/pbvi_ssea_agent.py:170, agents/pbvi_ger_agent.py:170, prune_level of every train(), agents/pbvi_agent.py:584-658):
@@ -286,6 +295,10 @@ typedef struct olfnav_sim_step_args {
      * both belief buffers hold belief_rows >= olfnav_fused_out_rows(m, n) rows. */
     int32_t* act_next;
     const int32_t* brow_in; int32_t* brow_out; int64_t belief_rows;
+    /* inplace = 1: ONE belief buffer (b_out == b_in, scale_out == scale_in): the survivors are updated in the rows they occupy and
+     * brow_out[j] = brow_in[src] carries where they are (10^6 agents x 30 793 states are 127 GB: two buffers do not fit one GPU).
+     * The caller runs the policy itself (have_act = 1), over all rows, and gathers the actions through the row map. */
+    int32_t inplace;
     /* layered environments (environment.py:202-235; simulation.py:1456-1463): layer of every action id (A ints, NULL without
      * layers), thresholds laid out [L][n_thr] when thr_per_layer = 1 (agent.py:414-417), L + 1 ints of scratch for time_mode 1 */
     const int32_t* act_layer; int32_t thr_per_layer; int32_t* hist_layer;

@@ -56,6 +56,8 @@ SIGNATURES = {
     'olfnav_backup_gamma': (_i, [_p, _p, _i64, _i, _f, _p, _i64, _p]),
     'olfnav_backup_select': (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p, _p, _i, _p]),
     'olfnav_backup_assemble': (_i, [_p, _p, _i64, _i, _p, _p, _i64, _p, _i64, _p]),
+    'olfnav_backup_select_alphas': (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _f, _p, _p, _p, _p]),
+    'olfnav_backup_assemble_alphas': (_i, [_p, _p, _i64, _i, _f, _p, _p, _i64, _p, _i64, _p]),
     'olfnav_vi_sweep': (_i, [_p, _p, _p, _i64, _d, _p, _p]),
     'olfnav_env_create': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _d, _d, _d]),
     'olfnav_env_create_layered': (_i, [ctypes.POINTER(_p), _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _d, _d, _d]),
@@ -84,7 +86,7 @@ class SimStepArgs(ctypes.Structure):
         ('counts', _p),
         ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
         ('act_next', _p),
-        ('brow_in', _p), ('brow_out', _p), ('belief_rows', _i64),
+        ('brow_in', _p), ('brow_out', _p), ('belief_rows', _i64), ('inplace', ctypes.c_int32),
         ('act_layer', _p), ('thr_per_layer', ctypes.c_int32), ('hist_layer', _p),
     ]
 

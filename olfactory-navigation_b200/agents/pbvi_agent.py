@@ -57,8 +57,14 @@ class BeliefSimulationMixin:
             b0[:n].copy_(src._b[:n])                   # never clobber the caller's set
             s0[:n].copy_(src._scale[:n])
         first = BeliefSet(model, _buffers=(b0, s0, n), device=device)
-        self._bufs = [first._b, torch.empty_like(first._b)]
-        self._scales = [first._scale, torch.zeros_like(first._scale)]
+        if getattr(self, '_single_buffer', False):
+            # run_test's in-place mode (10^6 agents x 30 793 states = 127 GB: a second buffer does not fit one B200): both "sides" of
+            # the ping-pong are the same tensor, rows never move
+            self._bufs = [first._b, first._b]
+            self._scales = [first._scale, first._scale]
+        else:
+            self._bufs = [first._b, torch.empty_like(first._b)]
+            self._scales = [first._scale, torch.zeros_like(first._scale)]
         self._cur = 0
         self._n_live = n
         self._ok = torch.empty(cap, dtype=torch.uint8, device=dev)

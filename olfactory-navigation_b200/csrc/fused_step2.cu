@@ -809,6 +809,7 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
     OLF_REQUIRE(ld >= m->g.Sp && (ld % 4) == 0, "belief_step_evaluate: ld must be >= Sp and a multiple of 4");
     OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL / 2, "belief_step_evaluate: n out of range");
     OLF_REQUIRE((((uintptr_t)b_in | (uintptr_t)b_out) & 15) == 0, "belief_step_evaluate: belief buffers must be 16-byte aligned");
+    if (n == 0) return OLFNAV_OK;
     if (!olfnav_can_fuse_policy(m, a)) {
         olfnav_set_error("belief_step_evaluate: needs <= %d alpha vectors, grid rows padded to 64 floats, wrapped vertical and clipped horizontal moves "
                          "(use belief_step + evaluate)", F2_MAX_BN);
@@ -816,7 +817,6 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
     }
     OLF_REQUIRE(rows_out >= olfnav_fused_out_rows(m, n), "belief_step_evaluate: b_out / scale_out need olfnav_fused_out_rows(m, n) rows");
     OLF_REQUIRE(rows_in >= 1, "belief_step_evaluate: rows_in");
-    if (n == 0) return OLFNAV_OK;
     OLF_CUDA(cudaSetDevice(m->device));
     const Geom& g = m->g;
     const int BN = a->Gp;

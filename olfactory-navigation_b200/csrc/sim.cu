@@ -189,6 +189,15 @@ __global__ void sim_gather_kernel(int n, const int* __restrict__ counts, const i
     ts_out[j] = ts_in[r];
 }
 
+// in-place update: survivor j keeps the belief row of the agent it was (rows never move)
+__global__ void sim_rows_kernel(int n, const int* __restrict__ counts, const int* __restrict__ src_rows, const int* __restrict__ brow_in,
+                                int* __restrict__ brow_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || j >= counts[0]) return;
+    const int r = src_rows[j];
+    brow_out[j] = brow_in ? brow_in[r] : r;
+}
+
 // failed updates / end of recording among the survivors: flag and count them (the caller does the rare second compaction)
 __global__ void sim_finish_kernel(int n, int* __restrict__ counts, const int* __restrict__ src_rows, const unsigned char* __restrict__ ok,
                                   const unsigned char* __restrict__ at_end, unsigned char* __restrict__ rec_term, unsigned char* __restrict__ term_c) {
@@ -209,7 +218,10 @@ __global__ void sim_finish_kernel(int n, int* __restrict__ counts, const int* __
 extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas, const olfnav_env* e,
                                const olfnav_sim_step_args* a, void* stream) {
     OLF_REQUIRE(m && e && a, "sim_step: null argument");
-    OLF_REQUIRE(a->b_in && a->b_out && a->b_in != a->b_out && a->scale_in && a->scale_out, "sim_step: belief buffers must be two distinct buffers");
+    OLF_REQUIRE(a->b_in && a->b_out && a->scale_in && a->scale_out, "sim_step: null belief buffer");
+    OLF_REQUIRE(a->b_in != a->b_out || (a->inplace && a->brow_out), "sim_step: one belief buffer needs inplace = 1 and brow_out (the rows stay where they are)");
+    OLF_REQUIRE(!a->inplace || (a->b_in == a->b_out && a->scale_in == a->scale_out && !a->act_next), "sim_step: inplace = 1 takes b_out == b_in, scale_out == scale_in and no one-pass policy");
+    OLF_REQUIRE(!a->inplace || a->have_act, "sim_step: inplace = 1 needs the caller's policy (have_act = 1): the actions are indexed by agent, the rows are not");
     OLF_REQUIRE(a->pos_in && a->pos_out && a->ts_in && a->ts_out && a->moves && a->thresholds, "sim_step: null state pointer");
     OLF_REQUIRE(a->act && a->obs_id && a->src_rows && a->act_c && a->obs_c && a->ok && a->at_end && a->term_c && a->counts, "sim_step: null scratch pointer");
     OLF_REQUIRE(a->rec_pos && a->rec_odor && a->rec_reached && a->rec_term, "sim_step: null record pointer");
@@ -277,6 +289,12 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
         OLF_REQUIRE(a->brow_out && a->belief_rows >= olfnav_fused_out_rows(m, n), "sim_step: the one-pass update needs brow_out and belief_rows >= olfnav_fused_out_rows");
         rc = olf_fused_step_launch(m, alphas, a->b_in, a->belief_rows, a->b_out, a->belief_rows, a->ld, n, a->act_c, a->obs_c, a->src_rows, a->brow_in,
                                    a->scale_in, a->scale_out, a->ok, nullptr, nullptr, a->act_next, a->brow_out, a->counts, st);
+    } else if (a->inplace) {
+        // one buffer: survivor j is updated in the row it already occupies (b_out == b_in with src == dst is safe, see belief.cu)
+        sim_rows_kernel<<<grid, 256, 0, st>>>(n, a->counts, a->src_rows, a->brow_in, a->brow_out);
+        OLF_LAUNCH_CHECK();
+        rc = olf_belief_step_launch(m, a->b_in, a->b_out, a->ld, n, a->act_c, a->obs_c, a->brow_out, a->brow_out, a->scale_in, a->scale_out,
+                                    a->ok, a->counts, stream);
     } else
         rc = olf_belief_step_launch(m, a->b_in, a->b_out, a->ld, n, a->act_c, a->obs_c, a->src_rows, nullptr, a->scale_in, a->scale_out,
                                     a->ok, a->counts, stream);

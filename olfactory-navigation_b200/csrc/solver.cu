@@ -133,6 +133,111 @@ __global__ void backup_assemble_kernel(const Geom g, const float* __restrict__ r
     *reinterpret_cast<float4*>(out + b * ld_out + 4 * (size_t)c) = acc;
 }
 
+// The FP16 split planes of Gamma built straight from the alpha vectors — Gamma itself is never written (at G = 512 it is 783 MB
+// of FP32 that the old path wrote, read back, and split: 1.24 of the 12.9 ms of a backup).  One CTA per Gamma row (a, o, g): pass 1
+// finds the row's maximum for the power-of-two scale, pass 2 recomputes the row (the alpha vector is L2 / L1 resident by then) and
+// writes b1 = fp16(t v), b2 = fp16((t v - b1) 2^11), binv = 1 / t (same scheme as split_planes_f16_kernel, same values: the row is
+// computed with the same operations as backup_gamma_kernel).  grid = (1, Gs, A * O), rows >= G of a segment are zero.
+__global__ void __launch_bounds__(256) gamma_planes_f16_kernel(const Geom g, const float* __restrict__ obs, const float* __restrict__ alpha,
+                                                               long long ld_alpha, int G, float discount, __half* __restrict__ b1,
+                                                               __half* __restrict__ b2, float* __restrict__ binv, long long ldh) {
+    __shared__ float red[8];
+    const int gi = blockIdx.y, ao = blockIdx.z;
+    const int a = ao / g.O, o = ao - a * g.O;
+    const long long dst = (long long)ao * gridDim.y + gi;
+    const bool live = gi < G;
+    const float* arow = alpha + (long long)gi * ld_alpha;
+    const float* ob = obs + ((size_t)(g.obs_per_action ? a : 0) * g.O + o) * g.Sp;
+    const int dy = g.moves[a][0], dx = g.moves[a][1];
+    // Gamma value at grid cell (y, x): (discount alpha(R_a(y, x))) O_o(R_a(y, x)), the operations of backup_gamma_kernel
+    auto value = [&](int y, int x) -> float {
+        const int d = bmove_dev(y, dy, g.H, g.wrap_y) * g.Wp + bmove_dev(x, dx, g.W, g.wrap_x);
+        return __fmul_rn(__fmul_rn(discount, arow[d]), __ldg(ob + d));
+    };
+    float mx = 0.f;
+    if (live)
+        for (int y = 0; y < g.H; ++y)
+            for (int x = threadIdx.x; x < g.W; x += blockDim.x) mx = fmaxf(mx, fabsf(value(y, x)));
+    for (int w = 16; w > 0; w >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, w));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    const float p2 = __uint_as_float(__float_as_uint(mx) & 0x7f800000u);
+    const float t = p2 > 0.f ? 8192.f / p2 : 1.f;
+    if (threadIdx.x == 0) binv[dst] = 1.f / t;
+    // two columns per thread: 32-bit stores of half pairs (Wp and ldh are even)
+    __half2* r1 = reinterpret_cast<__half2*>(b1 + dst * ldh);
+    __half2* r2 = reinterpret_cast<__half2*>(b2 + dst * ldh);
+    for (int y = 0; y < g.H; ++y)
+        for (int x = 2 * threadIdx.x; x < g.Wp; x += 2 * blockDim.x) {
+            const float v0 = (live && x < g.W) ? value(y, x) * t : 0.f;
+            const float v1 = (live && x + 1 < g.W) ? value(y, x + 1) * t : 0.f;
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const float2 f = __half22float2(h);
+            r1[(y * g.Wp + x) >> 1] = h;
+            r2[(y * g.Wp + x) >> 1] = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+        }
+    for (int c = g.Sp + 2 * threadIdx.x; c < ldh; c += 2 * blockDim.x) {          // columns beyond the padded row: zero
+        r1[c >> 1] = __floats2half2_rn(0.f, 0.f);
+        r2[c >> 1] = __floats2half2_rn(0.f, 0.f);
+    }
+}
+
+// alpha_new[b][:] = r_{a*} + sum_o Gamma[a*][o][g*(b,a*,o)][:] with the Gamma rows recomputed from the alpha vectors (same
+// operations, same order as backup_gamma_kernel + backup_assemble_kernel: bit-identical vectors)
+__global__ void backup_assemble_alphas_kernel(const Geom g, const float* __restrict__ reward, const float* __restrict__ obs,
+                                              const float* __restrict__ alpha, long long ld_alpha, float discount,
+                                              const int* __restrict__ best_g, const int* __restrict__ best_a, float* __restrict__ out,
+                                              long long ld_out) {
+    const long long b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    if (4 * c >= ld_out) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < g.Sp / 4) {
+        const int a = best_a[b];
+        acc = __ldg(reinterpret_cast<const float4*>(reward + (size_t)a * g.Sp) + c);
+        const int y = (g.W4 == 1) ? c : (int)__umulhi((unsigned)c, g.div_w4);
+        const int c4 = c - y * g.W4;
+        const int dy = g.moves[a][0], dx = g.moves[a][1];
+        const int y2 = bmove_dev(y, dy, g.H, g.wrap_y);
+        const float* ob = obs + (size_t)(g.obs_per_action ? a : 0) * g.O * g.Sp;
+        // products are rounded before they are added, like the Gamma rows the three-call path stores (no FMA contraction)
+        if (dx == 0) {
+            const int d4 = y2 * g.W4 + c4;                     // the destination cells of these four columns: one aligned float4
+            for (int o = 0; o < g.O; ++o) {
+                const int gi = best_g[(b * g.A + a) * g.O + o];
+                const float4 av = __ldg(reinterpret_cast<const float4*>(alpha + (long long)gi * ld_alpha) + d4);
+                const float4 l = __ldg(reinterpret_cast<const float4*>(ob + (size_t)o * g.Sp) + d4);
+                const bool px = 4 * c4 + 0 < g.W, py = 4 * c4 + 1 < g.W, pz = 4 * c4 + 2 < g.W, pw = 4 * c4 + 3 < g.W;
+                acc.x = __fadd_rn(acc.x, px ? __fmul_rn(__fmul_rn(discount, av.x), l.x) : 0.f);
+                acc.y = __fadd_rn(acc.y, py ? __fmul_rn(__fmul_rn(discount, av.y), l.y) : 0.f);
+                acc.z = __fadd_rn(acc.z, pz ? __fmul_rn(__fmul_rn(discount, av.z), l.z) : 0.f);
+                acc.w = __fadd_rn(acc.w, pw ? __fmul_rn(__fmul_rn(discount, av.w), l.w) : 0.f);
+            }
+        } else {
+            int d[4];
+            bool real[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int x = 4 * c4 + e;
+                real[e] = x < g.W;
+                d[e] = y2 * g.Wp + bmove_dev(real[e] ? x : 0, dx, g.W, g.wrap_x);
+            }
+            for (int o = 0; o < g.O; ++o) {
+                const int gi = best_g[(b * g.A + a) * g.O + o];
+                const float* ar = alpha + (long long)gi * ld_alpha;
+                const float* lr = ob + (size_t)o * g.Sp;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = real[e] ? __fmul_rn(__fmul_rn(discount, __ldg(ar + d[e])), __ldg(lr + d[e])) : 0.f;
+                acc.x = __fadd_rn(acc.x, v[0]); acc.y = __fadd_rn(acc.y, v[1]); acc.z = __fadd_rn(acc.z, v[2]); acc.w = __fadd_rn(acc.w, v[3]);
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(out + b * ld_out + 4 * (size_t)c) = acc;
+}
+
 // blockIdx.z = segment: source rows seg * rows .. + rows, destination rows seg * gridDim.y .. (segments padded to gridDim.y rows)
 __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, long long rows, int K,
                                     float* __restrict__ hi, float* __restrict__ lo, long long ld) {
@@ -183,6 +288,59 @@ extern "C" int olfnav_backup_gamma(const olfnav_model* m, const float* alpha, in
     if (m->dense) return olf_dense_backup_gamma(m, alpha, ld_alpha, G, discount, gamma_ao, ld_gamma, (cudaStream_t)stream);
     dim3 grid(olf_div_up(ld_gamma, 256), G, m->g.A);
     backup_gamma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m->g, m->obs, alpha, ld_alpha, G, discount, gamma_ao, ld_gamma);
+    OLF_LAUNCH_CHECK();
+    return OLFNAV_OK;
+}
+
+// Selection with the Gamma planes built straight from the alpha vectors (gamma_planes_f16_kernel): no FP32 Gamma in memory.
+extern "C" int olfnav_backup_select_alphas(const olfnav_model* m, const float* b, int64_t ld, int64_t n, const float* scale,
+                                           const float* alpha, int64_t ld_alpha, int G, float discount,
+                                           int32_t* best_g, int32_t* best_a, float* best_value, void* stream) {
+    OLF_REQUIRE(m && b && alpha && best_g && best_a, "backup_select_alphas: null argument");
+    OLF_REQUIRE(!m->dense, "backup_select_alphas: grid models only (dense models: olfnav_backup_gamma + olfnav_backup_select)");
+    OLF_REQUIRE(ld >= m->g.Sp && (ld % 4) == 0 && ld_alpha >= m->g.Sp, "backup_select_alphas: bad leading dimension");
+    OLF_REQUIRE(n >= 0 && n <= 0x7fffffffLL && G >= 1 && G <= 65535, "backup_select_alphas: bad n or G");
+    if (n == 0) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int A = m->g.A, O = m->g.O, nseg = A * O;
+    const int Gs = (G + 15) & ~15;
+    const long long ldh = (m->g.Sp + 63) & ~63;
+    OlfScratch s_seg(st), s_rew(st), s_arg(st), s_p1(st), s_p2(st), s_inv(st);
+    OLF_CUDA(s_seg.alloc((size_t)n * nseg * sizeof(float)));
+    OLF_CUDA(s_rew.alloc((size_t)n * A * sizeof(float)));
+    OLF_CUDA(s_arg.alloc((size_t)n * A * sizeof(int)));
+    OLF_CUDA(s_p1.alloc((size_t)nseg * Gs * ldh * sizeof(__half)));
+    OLF_CUDA(s_p2.alloc((size_t)nseg * Gs * ldh * sizeof(__half)));
+    OLF_CUDA(s_inv.alloc((size_t)nseg * Gs * sizeof(float)));
+    dim3 grid(1, Gs, nseg);
+    gamma_planes_f16_kernel<<<grid, 256, 0, st>>>(m->g, m->obs, alpha, ld_alpha, G, discount, s_p1.as<__half>(), s_p2.as<__half>(), s_inv.as<float>(), ldh);
+    OLF_LAUNCH_CHECK();
+    int rc = olf_umma_segmax_f16(b, ld, n, m->g.Sp, scale, s_p1.as<__half>(), s_p2.as<__half>(), s_inv.as<float>(), ldh, nseg * Gs, nseg, G, Gs,
+                                 s_seg.as<float>(), best_g, m->sm_count, st);
+    if (rc == OLFNAV_OK) rc = olf_segmax_simt(b, ld, n, m->g.Sp / 4, m->reward, m->g.Sp, A, 1, s_rew.as<float>(), s_arg.as<int>(), st);
+    if (rc == OLFNAV_OK) {
+        backup_pick_kernel<<<olf_div_up(n, 256), 256, 0, st>>>((int)n, A, O, scale, s_seg.as<float>(), s_rew.as<float>(), best_a, best_value);
+        OLF_LAUNCH_CHECK();
+    }
+    return rc;
+}
+
+extern "C" int olfnav_backup_assemble_alphas(const olfnav_model* m, const float* alpha, int64_t ld_alpha, int G, float discount,
+                                             const int32_t* best_g, const int32_t* best_a, int64_t n, float* alpha_new, int64_t ld_new,
+                                             void* stream) {
+    OLF_REQUIRE(m && alpha && best_g && best_a && alpha_new, "backup_assemble_alphas: null argument");
+    OLF_REQUIRE(!m->dense && ld_alpha >= m->g.Sp && (ld_alpha % 4) == 0 && ld_new >= m->g.Sp && (ld_new % 4) == 0 && G >= 1, "backup_assemble_alphas: bad argument");
+    OLF_REQUIRE((((uintptr_t)alpha | (uintptr_t)alpha_new) & 15) == 0, "backup_assemble_alphas: 16-byte aligned vectors");
+    if (n == 0) return OLFNAV_OK;
+    OLF_CUDA(cudaSetDevice(m->device));
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+        const int rows = (int)((n - r0 < 65535) ? (n - r0) : 65535);
+        dim3 grid(olf_div_up(ld_new / 4, 256), rows);
+        backup_assemble_alphas_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m->g, m->reward, m->obs, alpha, ld_alpha, discount,
+                                                                              best_g + r0 * m->g.A * m->g.O, best_a + r0,
+                                                                              alpha_new + r0 * ld_new, ld_new);
+    }
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
 }

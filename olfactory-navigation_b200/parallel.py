@@ -143,12 +143,12 @@ def backup_sharded(model, belief_set, alphas: torch.Tensor, gamma: float, path: 
         out_v = all_gather_rows(best_v[:, None], counts=counts)[0][:, 0].contiguous() if ws > 1 else best_v
         return out_alpha, out_a, out_v
     G = alphas.shape[0]
-    gam, best_g, best_a, best_v = backup_select_device(model, part, alphas, gamma, path)
+    ctx, best_g, best_a, best_v = backup_select_device(model, part, alphas, gamma, path)
     # (B_r, 2 + A*O) int32: best action, the value's bit pattern, the alpha indices
     packed = torch.cat([best_a[:, None], best_v.view(torch.int32)[:, None], best_g.reshape(hi - lo, -1)], dim=1).contiguous()
     packed_all, _ = all_gather_rows(packed, counts=counts)
     best_a_all = packed_all[:, 0].contiguous()
     best_v_all = packed_all[:, 1].contiguous().view(torch.float32)
     best_g_all = packed_all[:, 2:].contiguous()
-    new_alpha = backup_assemble_device(model, gam, G, best_g_all, best_a_all, belief_set.device)
+    new_alpha = backup_assemble_device(model, ctx, G, best_g_all, best_a_all, belief_set.device)
     return (new_alpha, best_a_all, best_v_all) if return_values else (new_alpha, best_a_all)

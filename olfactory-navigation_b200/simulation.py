@@ -548,6 +548,7 @@ def _run_batches(agent, n, start_points, time_shift, batches, **kw) -> Simulatio
 
 
 _PINNED = {}
+_SLEEP_ON_EVENTS = 2 * int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))) > (os.cpu_count() or 1)
 
 
 def _pinned(name: str, nbytes: int) -> torch.Tensor:
@@ -596,11 +597,24 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     # OLFNAV_FUSED_STEP=0 keeps the two kernels (belief step, then evaluate).
     fused = (not is_infotaxis and os.environ.get('OLFNAV_FUSED_STEP', '1') != '0'
              and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
+    # In-place mode: ONE belief buffer, the survivors are updated in the rows they occupy and a row map carries where they are.
+    # Chosen when two buffers do not fit the device (10^6 agents x 30 793 states = 127 GB of beliefs on a 180 GB part), or with
+    # OLFNAV_INPLACE=1; it takes the two-kernel step (the one-pass kernel writes the rows somewhere else by construction) and the
+    # policy runs over all rows, dead ones included, so it pays off only when memory forces it.
+    row_bytes = model.padded_states * 4
+    # free device memory + what torch's caching allocator holds without using it (the buffers of a previous run)
+    free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    inplace_env = os.environ.get('OLFNAV_INPLACE', '')
+    inplace = (inplace_env == '1') or (inplace_env != '0' and 2 * n * row_bytes > 0.92 * free_bytes >= n * row_bytes)
+    if inplace:
+        fused = False
     agent._row_capacity = int(lib.olfnav_fused_out_rows(model_h, n)) if fused else 0
+    agent._single_buffer = inplace
     try:
         agent.initialize_state(n, **initialization_values)
     finally:
         agent._row_capacity = 0
+        agent._single_buffer = False
     hist = SimulationHistory(start_points=start_points, environment=environment, agent=agent, time_shift=time_shift,
                              horizon=horizon, reward_discount=reward_discount, distance_metric=distance_metric, used_gpu=True)
 
@@ -663,8 +677,20 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                           reached_source=own['reached'].numpy()[:m_rec].view(np.bool_), interupt=own['term'].numpy()[:m_rec].view(np.bool_),
                           action_is_id=True)
 
-    def run_policy(b, scale, rows: int, act_out) -> None:
+    def run_policy(b, scale, rows: int, act_out, row_map=None) -> None:
         'argmax_g b.alpha_g -> action id (agents/pbvi_agent.py:741) or the infotaxis choice (agents/infotaxis_agent.py:244-301).'
+        if inplace:
+            # one buffer: the policy runs over every row the run started with (dead rows included: their results are never read),
+            # then the actions of the live agents are gathered through the row map
+            run_policy_rows(b, scale, n, act_by_row)
+            if row_map is None:
+                act_out[:rows].copy_(act_by_row[:rows])
+            else:
+                torch.index_select(act_by_row, 0, row_map[:rows].long(), out=act_out[:rows])
+            return
+        run_policy_rows(b, scale, rows, act_out)
+
+    def run_policy_rows(b, scale, rows: int, act_out) -> None:
         with torch.cuda.device(device):
             if is_infotaxis:
                 check(lib.olfnav_infotaxis_choose(model_h, b.data_ptr(), b.stride(0), rows, scale.data_ptr(), act_out.data_ptr(), None, stream()))
@@ -673,7 +699,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                                           int(getattr(agent, 'gemm_path', 0)), stream()))
 
     args = SimStepArgs()
-    brow = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
+    hist._step_mode = 'in_place' if inplace else ('one_pass' if fused else 'two_kernel')
+    brow = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if (fused or inplace) else None
+    act_by_row = torch.empty(cap, dtype=torch.int32, device=dev) if inplace else None       # in-place mode: policy output per belief ROW
     brow_valid = False                 # False: agent i's belief is row i (start of the run, or after an explicit compaction)
 
     act_next_buf = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
@@ -713,7 +741,17 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
         args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
         args.counts = counts.data_ptr()
-        if fused:
+        args.inplace = 1 if inplace else 0
+        if inplace:
+            if not have_act:
+                run_policy(b_cur, s_cur, n_live, r['act'], brow[cur] if brow_valid else None)      # first step: the caller's policy (see olfnav_sim_step)
+                have_act = True
+                args.have_act = 1
+            args.act_next = None
+            args.brow_in = brow[cur].data_ptr() if brow_valid else None
+            args.brow_out = brow[1 - cur].data_ptr()
+            args.belief_rows = int(b_cur.shape[0])
+        elif fused:
             # The update of this step also delivers the NEXT step's actions (also on the last step of the horizon: the policy rides
             # along for free).  They go to a buffer of their own and move into the record set at the start of the step that plays
             # them: the record set of step i + 1 is still on its way to the host while step i runs.
@@ -734,7 +772,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         with torch.cuda.device(device):
             check(lib.olfnav_sim_step(model_h, alphas_h, env_h, ctypes.byref(args), stream()))
         counts_host.copy_(counts, non_blocking=True)
-        step_done = torch.cuda.Event(blocking=True)        # the host sleeps (not spins) on it: 8 ranks share the host cores
+        # the one host wait of the step: sleep on it when the ranks of a node outnumber half the host cores (8 ranks share the cores of a
+        # node), spin otherwise (a blocking wake-up costs tens of microseconds of idle GPU per step)
+        step_done = torch.cuda.Event(blocking=_SLEEP_ON_EVENTS)
         step_done.record(main)
         if timing is not None:
             evs[4].record(main)
@@ -751,7 +791,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record(main)
             if not fused:
-                run_policy(b_nxt, s_nxt, n_live, nxt['act'])
+                run_policy(b_nxt, s_nxt, n_live, nxt['act'], brow[1 - cur] if inplace else None)
             if timing is not None:
                 p1.record(main)
                 evs += [p0, p1]
@@ -774,7 +814,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             timing.append((n_live, evs, m))
         agent._cur, agent._n_live, agent._action_ids, agent._dropped = 1 - agent._cur, m, None, None
         cur = 1 - cur
-        brow_valid = fused
+        brow_valid = fused or inplace
         if n_fail or n_end:
             # rare: some survivors must still go (impossible update / end of the recording): explicit compaction
             if fused and brow_valid:
@@ -782,6 +822,23 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 agent._rows_to_agent_order()
                 brow_valid = False
             keep = ~term_c[:m].bool()
+            if inplace:
+                # the belief rows stay where they are: only the bookkeeping (and the row map) is compacted
+                rows = torch.nonzero(keep).flatten()
+                k = int(rows.numel())
+                if k:
+                    pos[1 - cur][:k] = pos[cur][:m][rows]
+                    ts[1 - cur][:k] = ts[cur][:m][rows]
+                    brow[1 - cur][:k] = brow[cur][:m][rows]
+                    if have_act:
+                        nxt['act'][:k] = nxt['act'][:m][rows]
+                cur = 1 - cur
+                agent._n_live = k
+                n_live = k
+                flush(2)
+                if print_progress and hasattr(iterator, 'set_postfix'):
+                    iterator.set_postfix({'done ': f' {n - n_live}/{n}'})
+                continue
             rows = torch.nonzero(keep).flatten()
             k = int(rows.numel())
             if k:
@@ -802,6 +859,9 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         agent._bufs = None
     elif fused and brow_valid:
         agent._row_map = brow[cur][:n_live].clone()      # rows still grouped by action: put back in agent order on first use
+    elif inplace:
+        agent._bufs = None                               # one buffer, rows scattered: the state is not kept after an in-place run
+        agent._n_live = 0
     return hist
 
 

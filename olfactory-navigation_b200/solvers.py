@@ -117,44 +117,56 @@ class VI:
 
 
 # =================================================================================================
+def _gamma_free(model: POMDP, G: int, path: int) -> bool:
+    '''
+    Gamma-free backup (olfnav_backup_select_alphas / _assemble_alphas): the FP16 operand planes are built straight from the alpha
+    vectors and the selected Gamma rows recomputed at assembly — bit-identical vectors, no A*O*G*Sp floats in memory (783 MB at
+    G = 512, 3.1 GB at G = 2048).  Measured at B = 10 000, G = 512: selection 11.7 ms against 12.1 ms, assembly slower (the rows are
+    gathered through the move instead of streamed), so it is taken when Gamma would use more than a quarter of the free device memory,
+    or with OLFNAV_BACKUP_GAMMA=0; OLFNAV_BACKUP_GAMMA=1 always keeps Gamma in memory.  Tensor path of grid models from G = 128 up only.
+    '''
+    if model.dense or path == 1 or G < 128 or os.environ.get('OLFNAV_GEMM_F16', '1') == '0':
+        return False
+    flag = os.environ.get('OLFNAV_BACKUP_GAMMA', '')
+    if flag in ('0', '1'):
+        return flag == '0'
+    need = model.action_count * model.observation_count * G * model.padded_states * 4
+    return need > 0.25 * torch.cuda.mem_get_info(torch.device('cuda', current_device()))[0]
+
+
 def backup_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tensor, gamma: float, path: int = 0):
     '''
     One point-based backup of the alpha set `alphas` (G, Sp) at every belief of the set.
     Returns device tensors: new_alpha (B, Sp) f32, best_a (B,) i32, new_value (B,) f32 (value of the
     new vector at its belief), best_g (B, A, O) i32.
     '''
-    device = belief_set.device
-    dev = torch.device('cuda', device)
-    h = model.handle(device)
-    A, O, Sp = model.action_count, model.observation_count, model.padded_states
-    G, B = alphas.shape[0], len(belief_set)
-    gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=dev)
-    best_g = torch.empty((B, A, O), dtype=torch.int32, device=dev)
-    best_a = torch.empty(B, dtype=torch.int32, device=dev)
-    best_v = torch.empty(B, dtype=torch.float32, device=dev)
-    new_alpha = torch.empty((B, Sp), dtype=torch.float32, device=dev)
-    with torch.cuda.device(device):
-        check(lib.olfnav_backup_gamma(h, ptr(alphas), alphas.stride(0), G, gamma, ptr(gam), Sp, stream()))
-        check(lib.olfnav_backup_select(h, ptr(belief_set._b), belief_set.ld, B, ptr(belief_set._scale), ptr(gam), Sp, G,
-                                       ptr(best_g), ptr(best_a), ptr(best_v), path, stream()))
-        check(lib.olfnav_backup_assemble(h, ptr(gam), Sp, G, ptr(best_g), ptr(best_a), B, ptr(new_alpha), Sp, stream()))
+    ctx, best_g, best_a, best_v = backup_select_device(model, belief_set, alphas, gamma, path)
+    new_alpha = backup_assemble_device(model, ctx, alphas.shape[0], best_g, best_a, belief_set.device)
     return new_alpha, best_a, best_v, best_g
 
 
 def backup_select_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tensor, gamma: float, path: int = 0):
     '''
-    The first two thirds of backup_device: Gamma build + per-belief selection.  Returns (gam, best_g (B, A, O), best_a (B,), best_v (B,));
-    backup_assemble_device turns (gam, best_g, best_a) — of ANY belief points, e.g. gathered from other ranks — into alpha vectors.
+    The first two thirds of a backup: Gamma (or its operand planes) + per-belief selection.  Returns (ctx, best_g (B, A, O), best_a (B,),
+    best_v (B,)); backup_assemble_device turns (ctx, best_g, best_a) — of ANY belief points, e.g. gathered from other ranks — into
+    alpha vectors.  ctx is the FP32 Gamma tensor, or ('alphas', alphas, gamma) on the path that never materialises it.
     '''
     device = belief_set.device
     dev = torch.device('cuda', device)
     h = model.handle(device)
     A, O, Sp = model.action_count, model.observation_count, model.padded_states
     G, B = alphas.shape[0], len(belief_set)
-    gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=dev)
     best_g = torch.empty((max(B, 1), A, O), dtype=torch.int32, device=dev)
     best_a = torch.empty(max(B, 1), dtype=torch.int32, device=dev)
     best_v = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+    if _gamma_free(model, G, path):
+        alphas = alphas.contiguous()
+        if B:
+            with torch.cuda.device(device):
+                check(lib.olfnav_backup_select_alphas(h, ptr(belief_set._b), belief_set.ld, B, ptr(belief_set._scale), ptr(alphas), alphas.stride(0), G,
+                                                      gamma, ptr(best_g), ptr(best_a), ptr(best_v), stream()))
+        return ('alphas', alphas, gamma), best_g[:B], best_a[:B], best_v[:B]
+    gam = torch.empty((A * O * G, Sp), dtype=torch.float32, device=dev)
     with torch.cuda.device(device):
         check(lib.olfnav_backup_gamma(h, ptr(alphas), alphas.stride(0), G, gamma, ptr(gam), Sp, stream()))
         if B:
@@ -163,16 +175,22 @@ def backup_select_device(model: POMDP, belief_set: BeliefSet, alphas: torch.Tens
     return gam, best_g[:B], best_a[:B], best_v[:B]
 
 
-def backup_assemble_device(model: POMDP, gam: torch.Tensor, G: int, best_g: torch.Tensor, best_a: torch.Tensor, device: int = None):
-    'alpha_b = r_{a*} + sum_o Gamma[a*][o][g*(b, a*, o)] for every row of (best_g, best_a).'
+def backup_assemble_device(model: POMDP, ctx, G: int, best_g: torch.Tensor, best_a: torch.Tensor, device: int = None):
+    'alpha_b = r_{a*} + sum_o Gamma[a*][o][g*(b, a*, o)] for every row of (best_g, best_a); ctx from backup_select_device.'
     device = current_device() if device is None else device
     Sp = model.padded_states
     B = int(best_a.shape[0])
-    new_alpha = torch.empty((B, Sp), dtype=torch.float32, device=gam.device)
+    dev = ctx[1].device if isinstance(ctx, tuple) else ctx.device
+    new_alpha = torch.empty((B, Sp), dtype=torch.float32, device=dev)
     if B:
         with torch.cuda.device(device):
-            check(lib.olfnav_backup_assemble(model.handle(device), ptr(gam), Sp, G, ptr(best_g.contiguous()), ptr(best_a.contiguous()), B,
-                                             ptr(new_alpha), Sp, stream()))
+            if isinstance(ctx, tuple):
+                _, alphas, gamma = ctx
+                check(lib.olfnav_backup_assemble_alphas(model.handle(device), ptr(alphas), alphas.stride(0), G, gamma, ptr(best_g.contiguous()),
+                                                        ptr(best_a.contiguous()), B, ptr(new_alpha), Sp, stream()))
+            else:
+                check(lib.olfnav_backup_assemble(model.handle(device), ptr(ctx), Sp, G, ptr(best_g.contiguous()), ptr(best_a.contiguous()), B,
+                                                 ptr(new_alpha), Sp, stream()))
     return new_alpha
 
 

