@@ -39,7 +39,8 @@ N_AGENTS = 100_000
 WORKLOADS = {'C2': '55x247 plume + 14/62 margins = 83x371 = 30793 states, 4 actions, 3 observations, wrap_vertical',
              'C5': '110x494 plume + 28/124 margins = 166x742 = 123172 states, 4 actions, 3 observations, wrap_vertical'}
 # DRAM bytes per updated agent from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per launch / rows updated)
-TRAFFIC = {}
+TRAFFIC = {'fused2': ((12.809274e9 + 12.781066e9) / 100_000, 'profiles/r2p_ncu_full_raw_fused2.csv (C2, 100k agents, G=75: 12.81 GB read + 12.78 GB written per launch)'),
+           'belief_step': ((12.737818e9 + 12.680899e9) / 99_953, 'profiles/r2q_ncu_full_raw_belief_step.csv (C4 run, 99 953 live agents, rows padded to 384: 12.74 GB read + 12.68 GB written per launch)')}
 TRAIN = dict(expansions=10)          # the reference notebook's FSVI training call (experiments/pomdp_agent_training.ipynb cell 4)
 
 

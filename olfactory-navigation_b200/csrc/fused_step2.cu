@@ -61,7 +61,7 @@ constexpr int F2_PLAN_ITEMS = 4096;        // agents per CTA of the plan kernels
 struct F2Params {
     const float* b_in; long long ld;
     int KB, Sp, Wp, W;
-    int dbg;                               // OLFNAV_F2_DBG ablation bits: 1 no stores, 2 no MMAs, 4 no tensor-memory writes, 8 no update arithmetic, 16 no halo loads
+    int dbg;                               // OLFNAV_F2_DBG ablation bits: 1 no stores, 2 no MMAs, 4 no tensor-memory writes, 8 no update arithmetic
     int n_tiles_max; const int* n_tiles_dev;
     const int* tile_act;                   // [n_tiles_max]
     const int* slot_src;                   // [n_tiles_max * 128] belief row in b_in, -1 = empty slot
