@@ -302,6 +302,10 @@ typedef struct olfnav_sim_step_args {
     /* layered environments (environment.py:202-235; simulation.py:1456-1463): layer of every action id (A ints, NULL without
      * layers), thresholds laid out [L][n_thr] when thr_per_layer = 1 (agent.py:414-417), L + 1 ints of scratch for time_mode 1 */
     const int32_t* act_layer; int32_t thr_per_layer; int32_t* hist_layer;
+    /* optional cudaEvent_t recorded on `stream` right after the compaction plan, i.e. as soon as counts[0] (the survivors of this step)
+     * is final and before the belief update starts: a caller that copies counts[0] out on another stream behind this event knows the
+     * size of the NEXT step while this one is still running and can enqueue it without ever leaving the GPU idle */
+    void* ev_plan_done;
 } olfnav_sim_step_args;
 
 int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas /* NULL = infotaxis */, const olfnav_env* e,

@@ -87,7 +87,7 @@ class SimStepArgs(ctypes.Structure):
         ('ev_policy_end', _p), ('ev_update_begin', _p), ('ev_update_end', _p),
         ('act_next', _p),
         ('brow_in', _p), ('brow_out', _p), ('belief_rows', _i64), ('inplace', ctypes.c_int32),
-        ('act_layer', _p), ('thr_per_layer', ctypes.c_int32), ('hist_layer', _p),
+        ('act_layer', _p), ('thr_per_layer', ctypes.c_int32), ('hist_layer', _p), ('ev_plan_done', _p),
     ]
 
 

@@ -279,6 +279,7 @@ extern "C" int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alpha
         olf_count_launch(1);
     }
     OLF_LAUNCH_CHECK();
+    if (a->ev_plan_done) OLF_CUDA(cudaEventRecord((cudaEvent_t)a->ev_plan_done, st));
     sim_gather_kernel<<<grid, 256, 0, st>>>(n, a->counts, a->src_rows, a->act, a->obs_id, a->rec_pos, (const long long*)a->ts_in,
                                             a->act_c, a->obs_c, a->pos_out, (long long*)a->ts_out);
     OLF_LAUNCH_CHECK();

@@ -702,22 +702,33 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     hist._step_mode = 'in_place' if inplace else ('one_pass' if fused else 'two_kernel')
     brow = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if (fused or inplace) else None
     act_by_row = torch.empty(cap, dtype=torch.int32, device=dev) if inplace else None       # in-place mode: policy output per belief ROW
-    brow_valid = False                 # False: agent i's belief is row i (start of the run, or after an explicit compaction)
-
     act_next_buf = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)] if fused else None
 
-    n_live, cur = n, 0
-    have_act = False                   # the next step's actions were computed ahead of time (see the end of the loop body)
-    iterator = range(horizon)
-    if print_progress:
-        try:
-            from tqdm.auto import trange
-            iterator = trange(horizon)
-        except Exception:
-            pass
-    for i in iterator:
-        if n_live == 0:
-            break
+    # Running ahead.  The size of step i + 1 (the survivors of step i) is final as soon as step i's compaction plan has run, i.e. BEFORE
+    # its belief update starts: the library records an event there (ev_plan_done), a side stream copies counts[0] out behind it, and the
+    # host enqueues step i + 1 while step i is still running — the GPU never waits for the host between two steps.  What is not known
+    # yet at that point is whether step i will flag failed updates (normaliser 0) or agents at the end of the recording: step i + 1 is
+    # launched on the assumption that it does not, and DISCARDED when it does (it only writes buffers that are two steps old: the
+    # state after step i is intact), the explicit compaction runs and the step is launched again.  Not in in-place mode (a step
+    # overwrites its own input) and not with time_loop = False (agents reach the end of the recording at every step near the end).
+    # The per-step flags that a discarded step would overwrite are double-buffered (counts, term_c).
+    ahead = os.environ.get('OLFNAV_RUN_AHEAD', '1') != '0' and bool(time_loop) and not inplace
+    counts2 = [counts, torch.zeros(4, dtype=torch.int32, device=dev)]
+    counts_host2 = [counts_host, _pinned('counts1', 16).view(torch.int32)]
+    term_c2 = [term_c, u8()]
+    early_host = [_pinned(f'early{k}', 16).view(torch.int32) for k in range(2)]
+    side = torch.cuda.Stream(device=dev) if ahead else None
+    plan_events = []
+    for _ in range(2 if ahead else 0):
+        e = torch.cuda.Event()
+        e.record(main)                                             # creates the underlying cudaEvent_t handle
+        plan_events.append(e)
+
+    S = dict(cur=0, brow_valid=False, n_live=n)     # brow_valid False: agent i's belief is row i (start of the run, or after an explicit compaction)
+
+    def launch(i: int, n_in: int, have_act: bool) -> dict:
+        'Enqueue step i for the n_in live agents of the current state (no host synchronisation).'
+        cur, brow_valid = S['cur'], S['brow_valid']
         r = recs[i & 1]
         if rec_free[i & 1] is not None:
             main.wait_event(rec_free[i & 1])
@@ -727,7 +738,7 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.scale_in, args.scale_out = s_cur.data_ptr(), s_nxt.data_ptr()
         args.pos_in, args.pos_out = pos[cur].data_ptr(), pos[1 - cur].data_ptr()
         args.ts_in, args.ts_out = ts[cur].data_ptr(), ts[1 - cur].data_ptr()
-        args.n, args.step = n_live, i
+        args.n, args.step = n_in, i
         args.moves, args.thresholds, args.n_thr = moves.data_ptr(), thresholds.data_ptr(), int(thresholds.shape[-1])
         args.act_layer = act_layer.data_ptr() if layered else None
         args.hist_layer = hist_layer.data_ptr() if layered else None
@@ -737,15 +748,14 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
         args.eval_path = int(getattr(agent, 'gemm_path', 0))
         args.have_act = 1 if have_act else 0
         args.act, args.obs_id, args.src_rows, args.act_c, args.obs_c = r['act'].data_ptr(), obs_id.data_ptr(), src_rows.data_ptr(), act_c.data_ptr(), obs_c.data_ptr()
-        args.ok, args.at_end, args.term_c = ok.data_ptr(), at_end.data_ptr(), term_c.data_ptr()
+        args.ok, args.at_end, args.term_c = ok.data_ptr(), at_end.data_ptr(), term_c2[i & 1].data_ptr()
         args.hist, args.eval_val, args.eval_idx = hist_t.data_ptr(), eval_val.data_ptr(), eval_idx.data_ptr()
         args.rec_pos, args.rec_odor, args.rec_reached, args.rec_term = r['pos'].data_ptr(), r['odor'].data_ptr(), r['reached'].data_ptr(), r['term'].data_ptr()
-        args.counts = counts.data_ptr()
+        args.counts = counts2[i & 1].data_ptr()
         args.inplace = 1 if inplace else 0
         if inplace:
             if not have_act:
-                run_policy(b_cur, s_cur, n_live, r['act'], brow[cur] if brow_valid else None)      # first step: the caller's policy (see olfnav_sim_step)
-                have_act = True
+                run_policy(b_cur, s_cur, n_in, r['act'], brow[cur] if brow_valid else None)      # first step: the caller's policy (see olfnav_sim_step)
                 args.have_act = 1
             args.act_next = None
             args.brow_in = brow[cur].data_ptr() if brow_valid else None
@@ -756,34 +766,42 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
             # along for free).  They go to a buffer of their own and move into the record set at the start of the step that plays
             # them: the record set of step i + 1 is still on its way to the host while step i runs.
             if have_act:
-                r['act'][:n_live].copy_(act_next_buf[i & 1][:n_live], non_blocking=True)
+                r['act'][:n_in].copy_(act_next_buf[i & 1][:n_in], non_blocking=True)
             args.act_next = act_next_buf[(i + 1) & 1].data_ptr()
             args.brow_in = brow[cur].data_ptr() if brow_valid else None
             args.brow_out = brow[1 - cur].data_ptr()
             args.belief_rows = int(b_cur.shape[0])
         else:
             args.act_next = None
+        evs = None
         if timing is not None:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             for e in evs:
                 e.record(main)                                  # creates the underlying cudaEvent_t handles
             args.ev_policy_end, args.ev_update_begin, args.ev_update_end = evs[1].cuda_event, evs[2].cuda_event, evs[3].cuda_event
             evs[0].record(main)
+        run_ahead = ahead and i + 1 < horizon
+        args.ev_plan_done = plan_events[i & 1].cuda_event if run_ahead else None
         with torch.cuda.device(device):
             check(lib.olfnav_sim_step(model_h, alphas_h, env_h, ctypes.byref(args), stream()))
-        counts_host.copy_(counts, non_blocking=True)
-        # the one host wait of the step: sleep on it when the ranks of a node outnumber half the host cores (8 ranks share the cores of a
-        # node), spin otherwise (a blocking wake-up costs tens of microseconds of idle GPU per step)
+        counts_host2[i & 1].copy_(counts2[i & 1], non_blocking=True)
+        # the host wait of the step: sleep on it when the ranks of a node outnumber half the host cores (8 ranks share the cores of a
+        # node), spin otherwise (a blocking wake-up costs tens of microseconds)
         step_done = torch.cuda.Event(blocking=_SLEEP_ON_EVENTS)
         step_done.record(main)
         if timing is not None:
             evs[4].record(main)
+        early = None
+        if run_ahead:
+            with torch.cuda.stream(side):
+                side.wait_event(plan_events[i & 1])
+                early_host[i & 1][:1].copy_(counts2[i & 1][:1], non_blocking=True)
+                early = torch.cuda.Event(blocking=_SLEEP_ON_EVENTS)
+                early.record(side)
 
-        # Policy of the NEXT step, enqueued before the host waits for this step's survivor count: it runs over the n_live rows of
-        # the updated buffer (an upper bound of the survivors; rows are independent, the surplus results are never read) and keeps
-        # the GPU busy while the host reads the counts and prepares the next call.
-        have_act = i + 1 < horizon
-        if have_act:
+        # Two-kernel modes: the policy of the NEXT step, enqueued right behind this step: it runs over the n_in rows of the updated
+        # buffer (an upper bound of the survivors; rows are independent, the surplus results are never read).
+        if i + 1 < horizon:
             nxt = recs[(i + 1) & 1]
             if not fused and rec_free[(i + 1) & 1] is not None:
                 main.wait_event(rec_free[(i + 1) & 1])
@@ -791,12 +809,12 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 p0.record(main)
             if not fused:
-                run_policy(b_nxt, s_nxt, n_live, nxt['act'], brow[1 - cur] if inplace else None)
+                run_policy(b_nxt, s_nxt, n_in, nxt['act'], brow[1 - cur] if inplace else None)
             if timing is not None:
                 p1.record(main)
                 evs += [p0, p1]
 
-        # record of this step -> pinned host memory on the side stream
+        # record of this step -> pinned host memory on the side stream; the host consumes older records here, with the step enqueued
         if record:
             flush(2)                                             # the host set about to be overwritten has been consumed
             with torch.cuda.stream(copy_stream):
@@ -805,59 +823,88 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
                 copied = torch.cuda.Event(blocking=True)
                 copied.record(copy_stream)
             rec_free[i & 1] = copied
-            pending.append((copied, rec_host_views[i % 3], n_live))
-        hist._agent_steps = getattr(hist, '_agent_steps', 0) + n_live
+            pending.append((copied, rec_host_views[i % 3], n_in))
+        hist._agent_steps = getattr(hist, '_agent_steps', 0) + n_in
+        return dict(i=i, n=n_in, step_done=step_done, early=early, evs=evs)
 
-        step_done.synchronize()                                  # the one host sync of the step
-        m, n_fail, n_end = int(counts_host[0]), int(counts_host[1]), int(counts_host[2])
-        if timing is not None:
-            timing.append((n_live, evs, m))
+    def advance(m: int) -> None:
+        'The host-side state after a step that left m survivors.'
         agent._cur, agent._n_live, agent._action_ids, agent._dropped = 1 - agent._cur, m, None, None
-        cur = 1 - cur
-        brow_valid = fused or inplace
+        S['cur'] = 1 - S['cur']
+        S['brow_valid'] = fused or inplace
+        S['n_live'] = m
+
+    bar = None
+    if print_progress:
+        try:
+            from tqdm.auto import tqdm
+            bar = tqdm(total=horizon)
+        except Exception:
+            pass
+
+    info = launch(0, n, False) if (horizon > 0 and n > 0) else None
+    while info is not None:
+        i, nxt_info = info['i'], None
+        if info['early'] is not None:
+            # the survivors of step i are known while its belief update is still running: enqueue step i + 1 behind it
+            info['early'].synchronize()
+            m = int(early_host[i & 1][0])
+            advance(m)
+            if m > 0:
+                nxt_info = launch(i + 1, m, True)
+        info['step_done'].synchronize()
+        ch = counts_host2[i & 1]
+        m_done, n_fail, n_end = int(ch[0]), int(ch[1]), int(ch[2])
+        if info['early'] is None:
+            m = m_done
+            advance(m)
+        if timing is not None:
+            timing.append((info['n'], info['evs'], m))
         if n_fail or n_end:
-            # rare: some survivors must still go (impossible update / end of the recording): explicit compaction
-            if fused and brow_valid:
+            # rare: some survivors must still go (impossible update / end of the recording): explicit compaction of the state after
+            # step i.  A step that was enqueued ahead is discarded first (its outputs are overwritten by the launch that follows).
+            if nxt_info is not None:
+                if record:
+                    pending.pop()
+                hist._agent_steps -= nxt_info['n']
+                nxt_info = None
+            cur = S['cur']
+            have_next = i + 1 < horizon
+            if fused and S['brow_valid']:
                 agent._row_map = brow[cur]
                 agent._rows_to_agent_order()
-                brow_valid = False
-            keep = ~term_c[:m].bool()
-            if inplace:
-                # the belief rows stay where they are: only the bookkeeping (and the row map) is compacted
-                rows = torch.nonzero(keep).flatten()
-                k = int(rows.numel())
-                if k:
-                    pos[1 - cur][:k] = pos[cur][:m][rows]
-                    ts[1 - cur][:k] = ts[cur][:m][rows]
-                    brow[1 - cur][:k] = brow[cur][:m][rows]
-                    if have_act:
-                        nxt['act'][:k] = nxt['act'][:m][rows]
-                cur = 1 - cur
-                agent._n_live = k
-                n_live = k
-                flush(2)
-                if print_progress and hasattr(iterator, 'set_postfix'):
-                    iterator.set_postfix({'done ': f' {n - n_live}/{n}'})
-                continue
+                S['brow_valid'] = False
+            keep = ~term_c2[i & 1][:m].bool()
             rows = torch.nonzero(keep).flatten()
             k = int(rows.numel())
             if k:
                 pos[1 - cur][:k] = pos[cur][:m][rows]
                 ts[1 - cur][:k] = ts[cur][:m][rows]
-                if have_act:
-                    nact = act_next_buf[(i + 1) & 1] if fused else nxt['act']
+                if inplace:
+                    brow[1 - cur][:k] = brow[cur][:m][rows]       # the belief rows stay where they are: only the row map is compacted
+                if have_next:
+                    nact = act_next_buf[(i + 1) & 1] if fused else recs[(i + 1) & 1]['act']
                     nact[:k] = nact[:m][rows]
-            cur = 1 - cur
-            agent.kill_device(~keep)
+            S['cur'] = 1 - cur
+            if inplace:
+                agent._n_live = k
+            else:
+                agent.kill_device(~keep)
             m = k
-        n_live = m
-        flush(2)
-        if print_progress and hasattr(iterator, 'set_postfix'):
-            iterator.set_postfix({'done ': f' {n - n_live}/{n}'})
+            S['n_live'] = m
+        if bar is not None:
+            bar.update(1)
+            bar.set_postfix({'done ': f' {n - m}/{n}'})
+        if nxt_info is None and i + 1 < horizon and m > 0:
+            nxt_info = launch(i + 1, m, True)
+        info = nxt_info
+    if bar is not None:
+        bar.close()
     flush(0)
+    n_live, cur = S['n_live'], S['cur']
     if n_live == 0:
         agent._bufs = None
-    elif fused and brow_valid:
+    elif fused and S['brow_valid']:
         agent._row_map = brow[cur][:n_live].clone()      # rows still grouped by action: put back in agent order on first use
     elif inplace:
         agent._bufs = None                               # one buffer, rows scattered: the state is not kept after an in-place run

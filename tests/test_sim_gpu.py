@@ -410,6 +410,71 @@ def test_in_place_run_equals_two_buffer_run(cfg, monkeypatch):
     assert np.array_equal(np.array(got.actions), np.array(ref.actions)) and np.array_equal(got.done_at_step, ref.done_at_step)
 
 
+@pytest.mark.parametrize('fused', ['1', '0'])
+def test_run_ahead_discards_the_step_enqueued_behind_failed_updates(fused, monkeypatch):
+    '''
+    run_test enqueues step i + 1 as soon as step i's survivor count is known, i.e. before step i's belief update has said whether
+    any update was impossible.  Agents that start from a point mass in a margin corner cannot observe anything but "nothing": their
+    update fails at the first detection-level observation... here at step 0 for the ones seeded with an impossible prior, so the
+    step enqueued ahead must be thrown away, the survivors compacted and the step launched again.  Same history as the loop that
+    never runs ahead (OLFNAV_RUN_AHEAD=0) and as the host-driven protocol loop (reference step order, simulation.py:1452-1497), with
+    the one-pass kernel and with the two kernels.
+    '''
+    import olfactory_navigation_b200 as onb
+    monkeypatch.setenv('OLFNAV_ROW_PAD', '64')
+    monkeypatch.setenv('OLFNAV_FUSED_STEP', fused)
+    g = golden('runtest_fsvi_T1')
+    c = onb.synthetic.config('T1')
+    env = onb.Environment(**c['env_kwargs'])
+    agent = onb.agents.PBVI_Agent(env, thresholds=c['thresholds'])
+    agent.value_function = onb.ValueFunction(agent.model, g['alphas'].astype(np.float64), g['alpha_actions'])
+    m = agent.model
+    starts, tshift = g['start_points'].astype(int), g['time_shift'].astype(int)
+    n, horizon = len(starts), 20
+    # a third of the agents believe they sit in a cell whose successor cells can only ever emit observation 0: any other observation
+    # (they do get some: their true position is a real start point) makes the normaliser 0
+    prior = np.tile(m.start_probabilities, (n, 1))
+    obs_tab = np.asarray(m.observation_table)                       # (S, A, O)
+    quiet = (obs_tab[:, :, 0] == 1.0).all(axis=1)
+    R = np.asarray(m.reachable_states)[:, :, 0]                      # (S, A): the one successor of every move
+    silent = np.flatnonzero(quiet & quiet[R].all(axis=1))           # cells that stay silent for at least two moves
+    assert len(silent) > 0
+    for k in range(0, n, 3):
+        prior[k] = 0.0
+        prior[k, silent[k % len(silent)]] = 1.0
+    kw = dict(n=n, start_points=starts, time_shift=tshift, horizon=horizon, print_progress=False, print_stats=False, batches=1)
+    monkeypatch.setenv('OLFNAV_RUN_AHEAD', '1')
+    got = onb.run_test(agent, initialization_values=dict(belief=onb.BeliefSet(m, prior)), **kw)
+    monkeypatch.setenv('OLFNAV_RUN_AHEAD', '0')
+    ref = onb.run_test(agent, initialization_values=dict(belief=onb.BeliefSet(m, prior)), **kw)
+    for a, b in ((got.actions, ref.actions), (got.positions, ref.positions), (got.observations, ref.observations)):
+        assert len(a) == len(b) and all(np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True) for x, y in zip(a, b))
+    assert np.array_equal(got.done_at_step, ref.done_at_step) and np.array_equal(got.reached_source, ref.reached_source)
+    # the protocol loop
+    pos, ts = starts.copy(), tshift.copy()
+    agent.initialize_state(n, onb.BeliefSet(m, prior))
+    hist = onb.SimulationHistory(pos, env, agent, ts, horizon)
+    failed = 0
+    for i in range(horizon):
+        action = agent.choose_action()
+        pos = env.move(pos, action)
+        observation = env.get_observation(pos, time=ts + i)
+        reached = env.source_reached(pos)
+        ok = agent.update_state(action=action, observation=observation, source_reached=reached)
+        failed += int((~ok & ~reached).sum())
+        term = reached | ~ok
+        hist.add_step(actions=action, next_positions=pos, observations=observation, reached_source=reached, interupt=term)
+        pos, ts = pos[~term], ts[~term]
+        agent.kill(simulations_to_kill=term)
+        if len(pos) == 0:
+            break
+    assert failed > 0, 'the scenario must contain impossible updates'
+    assert np.array_equal(np.array(got.done_at_step), np.array(hist.done_at_step))
+    assert np.array_equal(np.array(got.reached_source), np.array(hist.reached_source))
+    for x, y in zip(got.positions, hist.positions):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
 def test_many_agents_compaction_across_plan_tiles():
     '''
     9 600 agents = 200 copies of the 48 golden start points (several 4 096-agent tiles of the compaction plan).  With every agent
