@@ -20,17 +20,18 @@
 //
 // Accuracy.  ΔH_a is a difference of terms of order one (the entropy of the observation and its conditional entropy) while the gaps
 // between actions that decide the argmax can be 1e-6 and less on flat beliefs: FP32 sums (1e-6 relative) cannot settle those.
-// The finish kernel therefore combines the sums in float64, bounds its own error per action (E_a = kappa (1 + H_o + |Σ b C|)) and
-// lists the agents whose best two actions are closer than the bounds; infotaxis_exact_kernel re-derives THEIR choice in float64 in
-// the well-conditioned form      ΔH_a = corr_a + Σ_s b(s) · KL( O(.|R_a(s)) || p_a ) ,   KL >= 0 term by term,
-// (two passes over the agent's row per action: p_a first, then the sum).  A caller that asks for the ΔH values themselves (dH != NULL,
-// diagnostics and tests) gets the float64 kernel for every agent.  Decisions therefore agree with a float64 evaluation of the
-// reference's formula (agents/infotaxis_agent.py:257-293) except at ties below 1e-9 relative.
+// The finish kernel therefore combines the sums in float64, bounds its own error per action (E_a = kappa (1 + H_o + |Σ b C| + |corr|)) and
+// lists the agents for which another action lies within the bounds of the best one, together with the mask of those actions;
+// infotaxis_exact_kernel re-derives the listed (agent, action) values with every sum in double (absolute error ~1e-14 on terms of order
+// one, both normalised by Σ_o p_o = Σ b like the fast path) and infotaxis_pick_kernel takes the first maximum among them.  A caller that
+// asks for the ΔH values themselves (dH != NULL, diagnostics and tests) gets the float64 kernels for every agent and action.  Decisions
+// therefore agree with a float64 evaluation of the reference's formula (agents/infotaxis_agent.py:257-293) except at ties below 1e-9 relative.
 #include "common.cuh"
 #include "stencil.cuh"
 #include "umma_gemm.cuh"
 
 #include <cstdlib>
+#include <algorithm>
 
 namespace {
 
@@ -119,7 +120,7 @@ constexpr int IF_WARPS = 8;
 __global__ void __launch_bounds__(IF_WARPS * 32)
 infotaxis_finish_kernel(const __grid_constant__ Geom g, int n, const float* __restrict__ b, long long ld, const float* __restrict__ scale,
                         const float* __restrict__ sums, int ld_sums, int* __restrict__ action, float* __restrict__ dH,
-                        float kappa, int* __restrict__ unsure_rows, int* __restrict__ unsure_count) {
+                        float kappa, int* __restrict__ unsure_rows, int* __restrict__ unsure_count, int* __restrict__ unsure_mask) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * IF_WARPS + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -186,9 +187,15 @@ infotaxis_finish_kernel(const __grid_constant__ Geom g, int n, const float* __re
     if (lane == 0) {
         action[row] = ba;
         // another action within the error bounds of the best one: float64 re-evaluation (infotaxis_exact_kernel)
-        bool unsure = false;
-        for (int a = 0; a < g.A; ++a) unsure |= (a != ba) && (best - d_all[a] <= best_err + e_all[a]);
-        if (unsure && unsure_rows) unsure_rows[atomicAdd(unsure_count, 1)] = (int)row;
+        // (only the actions inside the bounds take part: the others are lower for certain)
+        unsigned mask = 0;
+        for (int a = 0; a < g.A; ++a)
+            if (a == ba || best - d_all[a] <= best_err + e_all[a]) mask |= 1u << a;
+        if ((mask & (mask - 1)) && unsure_rows) {
+            const int k = atomicAdd(unsure_count, 1);
+            unsure_rows[k] = (int)row;
+            unsure_mask[k] = (int)mask;
+        }
     }
 }
 
@@ -221,104 +228,143 @@ __device__ __forceinline__ int bmove_d(int v, int d, int n, int wrap) {
     return v;
 }
 
-// float64 evaluation of the infotaxis choice of the agents listed in `rows` (count on the device) or of every agent (rows == NULL).
-// One CTA per agent; per action two passes over the agent's row (L2 resident after the first): p_{a,o} = Σ_s b(s) O_o(R_a(s)), then
-// I_a = Σ_s b(s) [C(R_a(s)) - Σ_o O_o(R_a(s)) log p_{a,o}] (every KL term >= 0), plus the entropy change corr_a of the push at
-// clipped edges.  obs_ent64 holds C(s') = Σ_o O_o log O_o in double.
+// float64 evaluation of ΔH_a for the agents listed in `rows` (count on the device; masks[j] = the actions of entry j that take part)
+// or for every agent and action (rows == NULL).  ΔH_a = -Σ_o p_o log p_o + Σ_s b(s) C(R_a(s)) + corr_a with p_o = Σ_s b(s) O_o(R_a(s)),
+// C = Σ_o O_o log O_o (obs_ent64, double) and corr_a the entropy change of the push at clipped edges: the same three terms as the FP32
+// path, every sum in double (absolute error ~1e-14 on terms of order one; the gaps this path is asked to settle are 1e-9 and up).
+// A CTA takes IX_ROWS list entries and ONE action, one pass over the rows: the likelihood and C tables of a cell (20 bytes per state and
+// action against 4 bytes of belief) are loaded once for the group — the path is bound by L2 traffic, and a thousand unsure agents must
+// not cost as much as the hundred thousand sure ones.  ΔH_a goes to dh64[entry * A + a]; infotaxis_pick_kernel takes the first maximum.
+constexpr int IX_ROWS = 4;
+template <int NO>
 __global__ void __launch_bounds__(IT_THREADS)
-infotaxis_exact_kernel(const __grid_constant__ Geom g, int n, const int* __restrict__ rows, const int* __restrict__ n_rows,
+infotaxis_exact_kernel(const __grid_constant__ Geom g, int n, const int* __restrict__ rows, const int* __restrict__ n_rows, const int* __restrict__ masks,
                        const float* __restrict__ b, long long ld, const float* __restrict__ scale, const float* __restrict__ obs,
-                       const double* __restrict__ obs_ent64, int* __restrict__ action, float* __restrict__ dH) {
+                       const double* __restrict__ obs_ent64, double* __restrict__ dh64) {
     __shared__ double red[33];
-    __shared__ double s_logp[IT_MAXO];
-    __shared__ double s_dh[OLFNAV_MAX_ACTIONS];
-    if (rows && (int)blockIdx.x >= *n_rows) return;
-    const long long row = rows ? rows[blockIdx.x] : blockIdx.x;
-    if (row >= n) return;
+    const int a = blockIdx.y;
     const int tid = threadIdx.x;
-    const double sc = scale ? (double)scale[row] : 1.0;
-    const float* bin = b + row * ld;
-    const int total = g.H * g.Wp;
-    for (int a = 0; a < g.A; ++a) {
-        const int dy = g.moves[a][0], dx = g.moves[a][1];
-        const int ae = g.obs_per_action ? a : 0;
-        const float* ot = obs + (size_t)ae * g.O * g.Sp;
-        const double* ce = obs_ent64 + (size_t)ae * g.Sp;
-        double P[IT_MAXO];
+    const int entries = rows ? min(*n_rows, n) : n;
+    const int dy = g.moves[a][0], dx = g.moves[a][1];
+    const int ae = g.obs_per_action ? a : 0;
+    const float* ot = obs + (size_t)ae * g.O * g.Sp;
+    const double* ce = obs_ent64 + (size_t)ae * g.Sp;
+    const bool my = dy != 0 && !g.wrap_y && g.H > 1, mx = dx != 0 && !g.wrap_x && g.W > 1;
+    // the grid is a fixed number of CTAs per action (the list is usually a percent of the agents), each walks the groups with the grid's stride
+    for (int j0 = blockIdx.x * IX_ROWS; j0 < entries; j0 += gridDim.x * IX_ROWS) {
+        const float* bin[IX_ROWS];
+        bool on[IX_ROWS];
+        bool any = false;
 #pragma unroll
-        for (int o = 0; o < IT_MAXO; ++o) P[o] = 0.0;
-        for (int s = tid; s < total; s += IT_THREADS) {
-            const int y = s / g.Wp, x = s - y * g.Wp;
-            if (x >= g.W) continue;
-            const double v = (double)bin[s];
-            if (v == 0.0) continue;
-            const int s2 = bmove_d(y, dy, g.H, g.wrap_y) * g.Wp + bmove_d(x, dx, g.W, g.wrap_x);
-#pragma unroll
-            for (int o = 0; o < IT_MAXO; ++o)
-                if (o < g.O) P[o] += v * (double)__ldg(ot + (size_t)o * g.Sp + s2);
+        for (int r = 0; r < IX_ROWS; ++r) {
+            const int j = j0 + r;
+            on[r] = j < entries && (!rows || ((masks[j] >> a) & 1));
+            const long long row = on[r] ? (rows ? rows[j] : j) : 0;
+            bin[r] = b + row * ld;
+            any |= on[r];
         }
+        if (!any) continue;
+        double P[IX_ROWS][NO], C[IX_ROWS];
 #pragma unroll
-        for (int o = 0; o < IT_MAXO; ++o) {
-            if (o < g.O) {
-                const double p = block_sum_d<IT_THREADS>(P[o], red) * sc;
-                if (tid == 0) s_logp[o] = p > 0.0 ? log(p) : 0.0;
+        for (int r = 0; r < IX_ROWS; ++r) {
+            C[r] = 0.0;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) P[r][o] = 0.0;
+        }
+        for (int y = 0; y < g.H; ++y) {
+            const int y2 = bmove_d(y, dy, g.H, g.wrap_y) * g.Wp;
+            for (int x = tid; x < g.W; x += IT_THREADS) {
+                const int s = y * g.Wp + x, s2 = y2 + bmove_d(x, dx, g.W, g.wrap_x);
+                double v[IX_ROWS];
+#pragma unroll
+                for (int r = 0; r < IX_ROWS; ++r) v[r] = on[r] ? (double)bin[r][s] : 0.0;
+                const double c = ce[s2];
+                double O[NO];
+#pragma unroll
+                for (int o = 0; o < NO; ++o) O[o] = o < g.O ? (double)__ldg(ot + (size_t)o * g.Sp + s2) : 0.0;
+                // (the FP64 pipe is what bounds this kernel: no multiply-add for observations the model does not have — NO is the
+                // model's count rounded up to 3 / 5 / 8 — nor for the empty rows of a group)
+#pragma unroll
+                for (int r = 0; r < IX_ROWS; ++r) {
+                    if (!on[r]) continue;
+                    C[r] += v[r] * c;
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) P[r][o] += v[r] * O[o];
+                }
             }
         }
-        __syncthreads();
-        double acc = 0.0;
-        for (int s = tid; s < total; s += IT_THREADS) {
-            const int y = s / g.Wp, x = s - y * g.Wp;
-            if (x >= g.W) continue;
-            const double v = (double)bin[s];
-            if (v == 0.0) continue;
-            const int s2 = bmove_d(y, dy, g.H, g.wrap_y) * g.Wp + bmove_d(x, dx, g.W, g.wrap_x);
-            double t = ce[s2];
 #pragma unroll
-            for (int o = 0; o < IT_MAXO; ++o)
-                if (o < g.O) t -= (double)__ldg(ot + (size_t)o * g.Sp + s2) * s_logp[o];
-            acc += v * t;
-        }
-        // entropy change of the push: cells of the clipped downstream edge lines receive themselves and their upstream neighbours
-        double corr = 0.0;
-        const bool my = dy != 0 && !g.wrap_y && g.H > 1, mx = dx != 0 && !g.wrap_x && g.W > 1;
-        if (my || mx) {
-            const int ey = dy > 0 ? g.H - 1 : 0, ex = dx > 0 ? g.W - 1 : 0;
-            const int n_line_y = my ? g.W : 0, n_line_x = mx ? g.H : 0;
-            for (int k = tid; k < n_line_y + n_line_x; k += IT_THREADS) {
-                int y, x;
-                if (k < n_line_y) { y = ey; x = k; } else { y = k - n_line_y; x = ex; if (my && y == ey) continue; }
-                double tot = 0.0, parts = 0.0;
-                for (int sy = -1; sy <= 0; ++sy)
-                    for (int sx = -1; sx <= 0; ++sx) {
-                        const int ys = (sy == 0) ? y : y - dy, xs = (sx == 0) ? x : x - dx;
-                        if (sy == 0 && !(my && y == ey) && dy != 0) continue;
-                        if (sx == 0 && !(mx && x == ex) && dx != 0) continue;
-                        if (sy == -1 && dy == 0) continue;
-                        if (sx == -1 && dx == 0) continue;
-                        int yy = ys, xx = xs;
-                        if (g.wrap_y) { if (yy < 0) yy += g.H; if (yy >= g.H) yy -= g.H; } else if (yy < 0 || yy >= g.H) continue;
-                        if (g.wrap_x) { if (xx < 0) xx += g.W; if (xx >= g.W) xx -= g.W; } else if (xx < 0 || xx >= g.W) continue;
-                        const double v = (double)bin[(size_t)yy * g.Wp + xx] * sc;
-                        tot += v;
-                        parts += xlogx_d(v);
-                    }
-                corr += xlogx_d(tot) - parts;
+        for (int r = 0; r < IX_ROWS; ++r) {
+            if (!on[r]) continue;                                   // uniform over the CTA
+            // entropy change of the push: cells of the clipped downstream edge lines receive themselves and their upstream neighbours
+            double corr = 0.0;
+            if (my || mx) {
+                const int ey = dy > 0 ? g.H - 1 : 0, ex = dx > 0 ? g.W - 1 : 0;
+                const int n_line_y = my ? g.W : 0, n_line_x = mx ? g.H : 0;
+                for (int k = tid; k < n_line_y + n_line_x; k += IT_THREADS) {
+                    int y, x;
+                    if (k < n_line_y) { y = ey; x = k; } else { y = k - n_line_y; x = ex; if (my && y == ey) continue; }
+                    double tot = 0.0, parts = 0.0;
+                    for (int sy = -1; sy <= 0; ++sy)
+                        for (int sx = -1; sx <= 0; ++sx) {
+                            const int ys = (sy == 0) ? y : y - dy, xs = (sx == 0) ? x : x - dx;
+                            if (sy == 0 && !(my && y == ey) && dy != 0) continue;
+                            if (sx == 0 && !(mx && x == ex) && dx != 0) continue;
+                            if (sy == -1 && dy == 0) continue;
+                            if (sx == -1 && dx == 0) continue;
+                            int yy = ys, xx = xs;
+                            if (g.wrap_y) { if (yy < 0) yy += g.H; if (yy >= g.H) yy -= g.H; } else if (yy < 0 || yy >= g.H) continue;
+                            if (g.wrap_x) { if (xx < 0) xx += g.W; if (xx >= g.W) xx -= g.W; } else if (xx < 0 || xx >= g.W) continue;
+                            const double v = (double)bin[r][(size_t)yy * g.Wp + xx];
+                            tot += v;
+                            parts += xlogx_d(v);
+                        }
+                    corr += xlogx_d(tot) - parts;          // of the UNNORMALISED row: k (x log x)(tot) - Σ k (x log x)(v) = k [same of the raw values], tot = Σ v
+                }
             }
+            // Σ_o p_o = Σ_s b(s) exactly (Σ_o O_o = 1 everywhere): everything is normalised by that sum, like the fast path — the row then
+            // sums to one to the last bit, whatever the few ulps between its carried FP32 scale and 1 / Σ b
+            const double lin = block_sum_d<IT_THREADS>(C[r] + corr, red);
+            double p[NO], psum = 0.0;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                p[o] = o < g.O ? block_sum_d<IT_THREADS>(P[r][o], red) : 0.0;
+                psum += p[o];
+            }
+            const double pinv = psum > 0.0 ? 1.0 / psum : 0.0;
+            double d = lin * pinv;
+#pragma unroll
+            for (int o = 0; o < NO; ++o)
+                if (o < g.O) d -= xlogx_d(p[o] * pinv);
+            if (tid == 0) dh64[(size_t)(j0 + r) * g.A + a] = d;
         }
-        const double d = block_sum_d<IT_THREADS>(acc * sc + corr, red);
-        if (tid == 0) s_dh[a] = d;
     }
-    __syncthreads();
-    if (tid == 0) {
-        double best = -INFINITY;
-        int ba = -1;
-        for (int a = 0; a < g.A; ++a) {
-            const double d = s_dh[a];
-            if (dH) dH[row * g.A + a] = (float)d;
-            if (best < d) { best = d; ba = a; }     // strict '<' : first maximum (infotaxis_agent.py:289)
-        }
-        action[row] = ba;
+}
+
+// first maximum of the float64 values of an entry's participating actions (strict '<': infotaxis_agent.py:289)
+__global__ void infotaxis_pick_kernel(int A, int n, const int* __restrict__ rows, const int* __restrict__ n_rows, const int* __restrict__ masks,
+                                      const double* __restrict__ dh64, int* __restrict__ action, float* __restrict__ dH) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || (rows && j >= *n_rows)) return;
+    const long long row = rows ? rows[j] : j;
+    const unsigned mask = rows ? (unsigned)masks[j] : 0xffffffffu;
+    double best = -INFINITY;
+    int ba = -1;
+    for (int a = 0; a < A; ++a) {
+        if (!((mask >> a) & 1)) continue;
+        const double d = dh64[(size_t)j * A + a];
+        if (dH) dH[row * A + a] = (float)d;
+        if (best < d) { best = d; ba = a; }
     }
+    action[row] = ba;
+}
+
+void launch_exact(const olfnav_model* m, int64_t n, const int* rows, const int* n_rows, const int* masks, const float* b, int64_t ld,
+                  const float* scale, double* dh64, cudaStream_t st) {
+    const dim3 grid((unsigned)std::min<int64_t>(olf_div_up(n, IX_ROWS), (int64_t)m->sm_count * 8), m->g.A);
+    if (m->g.O <= 3)      infotaxis_exact_kernel<3><<<grid, IT_THREADS, 0, st>>>(m->g, (int)n, rows, n_rows, masks, b, ld, scale, m->obs, m->obs_ent64, dh64);
+    else if (m->g.O <= 5) infotaxis_exact_kernel<5><<<grid, IT_THREADS, 0, st>>>(m->g, (int)n, rows, n_rows, masks, b, ld, scale, m->obs, m->obs_ent64, dh64);
+    else                  infotaxis_exact_kernel<8><<<grid, IT_THREADS, 0, st>>>(m->g, (int)n, rows, n_rows, masks, b, ld, scale, m->obs, m->obs_ent64, dh64);
 }
 
 }  // namespace
@@ -334,19 +380,25 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
     static const bool force_v1 = [] { const char* e = getenv("OLFNAV_INFOTAXIS_V1"); return e && e[0] == '1'; }();
     const bool exact_ok = m->obs_ent64 && m->g.O <= IT_MAXO;
     if (dH && exact_ok && !force_v1) {
-        // the values themselves are asked for (diagnostics, tests): float64 for every agent
-        infotaxis_exact_kernel<<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, (int)n, nullptr, nullptr, b, ld, scale, m->obs, m->obs_ent64, action, dH);
+        // the values themselves are asked for (diagnostics, tests): float64 for every agent and action
+        OlfScratch s_dh(st);
+        OLF_CUDA(s_dh.alloc((size_t)n * m->g.A * sizeof(double)));
+        launch_exact(m, n, nullptr, nullptr, nullptr, b, ld, scale, s_dh.as<double>(), st);
+        OLF_LAUNCH_CHECK();
+        infotaxis_pick_kernel<<<olf_div_up(n, 256), 256, 0, st>>>(m->g.A, (int)n, nullptr, nullptr, nullptr, s_dh.as<double>(), action, dH);
         OLF_LAUNCH_CHECK();
         return OLFNAV_OK;
     }
     if (!force_v1 && m->pull_rows <= 128) {
         const int ld_sums = m->pull_rows;
-        OlfScratch s_sums(st), s_list(st);
+        OlfScratch s_sums(st), s_list(st), s_dh(st);
         OLF_CUDA(s_sums.alloc((size_t)n * ld_sums * sizeof(float)));
         float* sums = s_sums.as<float>();
         int* list = nullptr;
         if (exact_ok) {
-            OLF_CUDA(s_list.alloc(((size_t)n + 1) * sizeof(int)));
+            // rows [0, n) | count [n] | action masks [n + 1, 2n + 1); float64 values of the listed (entry, action) pairs
+            OLF_CUDA(s_list.alloc((2 * (size_t)n + 1) * sizeof(int)));
+            OLF_CUDA(s_dh.alloc((size_t)n * m->g.A * sizeof(double)));
             list = s_list.as<int>();
             OLF_CUDA(cudaMemsetAsync(list + n, 0, sizeof(int), st));
         }
@@ -356,13 +408,14 @@ extern "C" int olfnav_infotaxis_choose(const olfnav_model* m, const float* b, in
         int rc = olf_umma_store(b, ld, n, m->g.Sp, m->pull_hi, m->pull_lo, m->pull_ld, m->pull_rows, sums, ld_sums, m->sm_count, st);
         if (rc == OLFNAV_OK) {
             infotaxis_finish_kernel<<<olf_div_up(n, IF_WARPS), IF_WARPS * 32, 0, st>>>(m->g, (int)n, b, ld, scale, sums, ld_sums, action, dH, kappa,
-                                                                                      kappa > 0.f ? list : nullptr, list ? list + n : nullptr);
+                                                                                      kappa > 0.f ? list : nullptr, list ? list + n : nullptr, list ? list + n + 1 : nullptr);
             olf_count_launch(1);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("infotaxis_choose: finish kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
         if (rc == OLFNAV_OK && list && kappa > 0.f) {
-            infotaxis_exact_kernel<<<(unsigned)n, IT_THREADS, 0, st>>>(m->g, (int)n, list, list + n, b, ld, scale, m->obs, m->obs_ent64, action, nullptr);
-            olf_count_launch(1);
+            launch_exact(m, n, list, list + n, list + n + 1, b, ld, scale, s_dh.as<double>(), st);
+            infotaxis_pick_kernel<<<olf_div_up(n, 256), 256, 0, st>>>(m->g.A, (int)n, list, list + n, list + n + 1, s_dh.as<double>(), action, nullptr);
+            olf_count_launch(2);
             if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("infotaxis_choose: exact kernel launch failed"); rc = OLFNAV_ERR_CUDA; }
         }
         if (rc == OLFNAV_OK && list && m->it_unsure) OLF_CUDA(cudaMemcpyAsync(m->it_unsure, list + n, sizeof(int), cudaMemcpyDeviceToDevice, st));
