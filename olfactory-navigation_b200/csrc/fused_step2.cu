@@ -780,6 +780,29 @@ int f2_launch(const CUtensorMap& tIn, const CUtensorMap& tOut, const CUtensorMap
 
 }  // namespace
 
+// Watchdog record of the one-pass kernel in mapped host memory (see mbar_watchdog_fire): 8 ints per process, set up on first use.
+static int* g_f2_wd_host = nullptr;
+static int f2_watchdog_setup() {
+    static OlfPerDeviceOnce once;
+    if (!g_f2_wd_host) {
+        OLF_CUDA(cudaHostAlloc((void**)&g_f2_wd_host, 8 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(g_f2_wd_host, 0, 8 * sizeof(int));
+    }
+    if (once.first()) {
+        int* dptr = nullptr;
+        OLF_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_f2_wd_host, 0));
+        OLF_CUDA(cudaMemcpyToSymbol(olf_wd_host, &dptr, sizeof(dptr)));
+    }
+    return OLFNAV_OK;
+}
+
+// out[0] != 0: an mbarrier wait of the one-pass kernel timed out in this process; out[1..5] = block, thread, barrier (shared-memory
+// address), parity, waited clocks >> 20.  Readable after the CUDA context has died.
+extern "C" int olfnav_debug_watchdog(int32_t* out) {
+    for (int k = 0; k < 8; ++k) out[k] = g_f2_wd_host ? g_f2_wd_host[k] : 0;
+    return OLFNAV_OK;
+}
+
 extern "C" int olfnav_can_fuse_policy(const olfnav_model* m, const olfnav_alphas* a) {
     if (!m || !a || m->dense || !a->h1 || a->Gp > F2_MAX_BN || !m->coef) return 0;
     const Geom& g = m->g;
@@ -818,6 +841,7 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
     OLF_REQUIRE(rows_out >= olfnav_fused_out_rows(m, n), "belief_step_evaluate: b_out / scale_out need olfnav_fused_out_rows(m, n) rows");
     OLF_REQUIRE(rows_in >= 1, "belief_step_evaluate: rows_in");
     OLF_CUDA(cudaSetDevice(m->device));
+    { const int wrc = f2_watchdog_setup(); if (wrc != OLFNAV_OK) return wrc; }
     const Geom& g = m->g;
     const int BN = a->Gp;
     const int n_tiles_max = (int)(olfnav_fused_out_rows(m, n) / BM);

@@ -642,6 +642,263 @@ umma_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
+// ============================================================================================================
+// CTA-PAIR variant of the FP16 split kernel (cta_group::2) for the large backup GEMMs.  umma_f16_kernel<128,...> pulls 64 KB through
+// L2 -> shared memory per K block and SM for 768 tensor-core cycles: at full tensor rate that is 24.8 TB/s over the chip, twice what
+// the L2 delivers (~6 300 B/clk = 12.4 TB/s: ncu showed 12.6 TB/s at 53 % tensor-pipe activity — the kernel sits on that ceiling).
+// Two CTAs of a cluster (the two SMs of a TPC) share one tile of B: the work unit is 256 rows x BN columns, each CTA loads and
+// transforms its own 128 rows of A (raw FP32 -> FP16 pairs in ITS tensor memory), loads HALF of the two B planes (BN / 2 rows) into
+// ITS shared memory, the leader issues ONE tcgen05.mma.cta_group::2 of M = 256 per step, and each CTA's accumulator (its 128 rows x
+// BN columns) lands in its own tensor memory: 48 KB per K block and SM instead of 64 (-25 % L2 traffic per flop).
+// Barriers: fullA / empty / aempty / tfull are per CTA (tcgen05.commit multicasts to both); fullB / ready / tempty live in the
+// leader and the peer's TMA engine, transform warps and epilogue warps arrive on them through the cluster address space.
+// One K block per accumulator lifetime (12 MMAs), no K split of a last partial wave (the caller only takes this kernel when there
+// are many waves).
+template <int BN, int STAGES, int TA>
+struct SmemLayoutP {
+    static constexpr int B_HALF_BYTES = (BN / 2) * 128;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES_H + 2 * B_HALF_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int A_BASE = 256;
+    static constexpr int NUM_BARS = 4 * STAGES + 4 + TA;
+    static_assert(A_BASE + 64 * TA <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
+    static_assert(TOTAL <= 227 * 1024 && 8 * NUM_BARS + 8 <= 256, "shared memory budget");
+};
+
+template <int BN, int STAGES, int TA>
+__global__ void __launch_bounds__(NTHREADS_H, 1)
+umma_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                     const __grid_constant__ CUtensorMap tmB2, const GemmParams p, const float* __restrict__ a_scale,
+                     const float* __restrict__ binv) {
+    using L = SmemLayoutP<BN, STAGES, TA>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+
+    auto a_raw = [&](int s) { return base + s * L::STAGE_BYTES; };
+    auto b_1 = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES_H; };
+    auto b_2 = [&](int s) { return base + s * L::STAGE_BYTES + A_TILE_BYTES_H + L::B_HALF_BYTES; };
+    const uint32_t bars = base + L::BAR_OFFSET;
+    auto bar_fullA = [&](int s) { return bars + 8 * s; };
+    auto bar_fullB = [&](int s) { return bars + 8 * (STAGES + s); };                 // leader's copy is the one in use
+    auto bar_ready = [&](int s) { return bars + 8 * (2 * STAGES + s); };             // leader's copy
+    auto bar_empty = [&](int s) { return bars + 8 * (3 * STAGES + s); };
+    auto bar_tfull = [&](int a) { return bars + 8 * (4 * STAGES + a); };
+    auto bar_tempty = [&](int a) { return bars + 8 * (4 * STAGES + 2 + a); };        // leader's copy
+    auto bar_aempty = [&](int a) { return bars + 8 * (4 * STAGES + 4 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L::BAR_OFFSET + 8 * L::NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    constexpr uint32_t TMEM_COLS = 512;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB2) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_fullA(s), 1); mbar_init(bar_fullB(s), 1); mbar_init(bar_ready(s), 16); mbar_init(bar_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 8); }
+        for (int a = 0; a < TA; ++a) mbar_init(bar_aempty(a), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // the peer's barriers are initialised and its tensor memory allocated before anything crosses
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs): own rows of A, own half of the B planes =====================
+        if (elect_one_sync()) {
+            const uint32_t leader_fullB0 = mapa_rank(bar_fullB(0), 0);
+            uint32_t it = 0;
+            for (int u = cluster_id; u < p.num_units; u += n_clusters) {
+                int mt, nt;
+                unit_to_tile(p, u, mt, nt);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(bar_empty(s), ph ^ 1);
+                    mbar_expect_tx(bar_fullA(s), A_TILE_BYTES_H);
+                    tma_load_2d(a_raw(s), &tmA, kb * BKH, mt * 2 * BM + (int)rank * BM, bar_fullA(s));
+                    tma_load_2d(a_raw(s) + A_TILE_BYTES, &tmA, kb * BKH + BK, mt * 2 * BM + (int)rank * BM, bar_fullA(s));
+                    if (leader) mbar_expect_tx(bar_fullB(s), 4 * L::B_HALF_BYTES);          // two planes x two CTAs
+                    tma_load_2d_pair(b_1(s), &tmB1, kb * BKH, nt * BN + (int)rank * (BN / 2), leader_fullB0 + 8 * s);
+                    tma_load_2d_pair(b_2(s), &tmB2, kb * BKH, nt * BN + (int)rank * (BN / 2), leader_fullB0 + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader only): M = 256 over both CTAs =====================
+        constexpr uint32_t idesc = make_idesc_f16_pair<BN>();
+        uint32_t it = 0;
+        for (int u = cluster_id; u < p.num_units; u += n_clusters) {
+            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                const int acc = it & 1;
+                const int s = it % STAGES;
+                mbar_wait_cluster(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+                mbar_wait_cluster(bar_ready(s), (it / STAGES) & 1);
+                mbar_wait_cluster(bar_fullB(s), (it / STAGES) & 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const int ta = it % TA;
+                    const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta, a2 = a1 + 32;
+                    const uint64_t db1 = make_sw128_desc(b_1(s)), db2 = make_sw128_desc(b_2(s));
+#pragma unroll
+                    for (int kk = 0; kk < BKH / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                        tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
+                        tc_mma_f16_ts_pair(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < BKH / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                        if (kk == 0) tc_mma_f16_ts_pair_scale11(d_tmem, a1, db1, idesc);
+                        else tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                    }
+                    tc_commit_pair(bar_empty(s));
+                    tc_commit_pair(bar_aempty(ta));
+                    tc_commit_pair(bar_tfull(acc));
+                }
+                __syncwarp();
+            }
+        }
+    }
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        // ===================== A transform (both CTAs): own rows -> FP16 pairs in own tensor memory, arrival on the leader =====================
+        const int t = (threadIdx.x - 128) & 127;
+        const int sub = (threadIdx.x - 128) >> 7;
+        const uint8_t* rowp = gbase + t * 128 + sub * A_TILE_BYTES;
+        const int sw = t & 7;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t leader_ready0 = mapa_rank(bar_ready(0), 0);
+        uint32_t it = 0;
+        for (int u = cluster_id; u < p.num_units; u += n_clusters) {
+            int mt, nt;
+            unit_to_tile(p, u, mt, nt);
+            const long long row = (long long)mt * 2 * BM + rank * BM + t;
+            const float sc = row_scale_pow2(a_scale, row, row < p.n_rows);
+            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int ta = it % TA;
+                mbar_wait(bar_fullA(s), ph);
+                mbar_wait(bar_aempty(ta), ((it / TA) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t th = tmem_base + lane_base + L::A_BASE + 64 * ta;
+                {
+                    const uint8_t* src = rowp + s * L::STAGE_BYTES;
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
+                        const float x0 = v.x * sc, x1 = v.y * sc, x2 = v.z * sc, x3 = v.w * sc;
+                        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.f, (x1 - f01.y) * 2048.f);
+                        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.f, (x3 - f23.y) * 2048.f);
+                        h[2 * c] = *reinterpret_cast<const uint32_t*>(&h01);
+                        h[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                        l[2 * c] = *reinterpret_cast<const uint32_t*>(&l01);
+                        l[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    }
+                    tc_st16(th + sub * 16, h);
+                    tc_st16(th + 32 + sub * 16, l);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_ready0 + 8 * s);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ===================== epilogue (both CTAs): own 128 rows of the accumulator =====================
+        const int q = warp & 3;
+        const bool direct = p.ws == nullptr;
+        const uint32_t leader_tempty0 = mapa_rank(bar_tempty(0), 0);
+        uint32_t it = 0;
+        for (int u = cluster_id; u < p.num_units; u += n_clusters) {
+            int mt, nt;
+            unit_to_tile(p, u, mt, nt);
+            const long long row = (long long)mt * 2 * BM + rank * BM + q * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            const int col0 = nt * BN;
+            int cur_seg = col0 / p.seg_stride, r = col0 - cur_seg * p.seg_stride;
+            float best = -INFINITY;
+            int best_idx = 0;
+            bool dirty = false;
+            float sum[BN];
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] = 0.f;
+            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+                const int acc = it & 1;
+                mbar_wait(bar_tfull(acc), (it >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t v[16];
+                    tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8 * acc);
+            }
+            const float inv_s = 1.f / row_scale_pow2(a_scale, row, row_ok);
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sum[j] *= inv_s * ((col0 + j < p.rows_b) ? __ldg(binv + col0 + j) : 0.f);
+            auto flush = [&]() {
+                if (row_ok && cur_seg < p.n_seg) {
+                    if (direct) {
+                        p.out_val[row * p.n_seg + cur_seg] = best;
+                        p.out_arg[row * p.n_seg + cur_seg] = best_idx;
+                    } else if (dirty) {
+                        atomicMax(p.ws + row * p.n_seg + cur_seg, pack_key(best, best_idx));
+                    }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+                const float x = sum[j];
+                if (r < p.seg_len && cur_seg < p.n_seg) {
+                    dirty = true;
+                    if (x > best) { best = x; best_idx = r; }
+                }
+                if (++r == p.seg_stride) {
+                    flush();
+                    r = 0; ++cur_seg; best = -INFINITY; best_idx = 0; dirty = false;
+                }
+            }
+            if (r != 0 && !direct) flush();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // neither CTA leaves (or frees its tensor memory) while the other may still touch it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
 
 // ws -> (value, first index); entries no unit touched stay (-inf, 0)
 __global__ void segmax_decode_kernel(long long n, const unsigned long long* __restrict__ ws, float* __restrict__ out_val,
@@ -912,7 +1169,15 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     static const int wide_bn = [] { const char* e = getenv("OLFNAV_GEMM_F16_BN"); const int v = e ? atoi(e) : 128; return (v == 80 || v == 96) ? v : 128; }();
     const int BN = rows_b <= 80 ? ((rows_b + 15) & ~15) : wide_bn;
     p.n_rows = (int)n_rows; p.K = K;
-    p.num_m_tiles = olf_div_up(n_rows, BM);
+    // CTA pairs (umma_f16_pair_kernel: 256-row tiles, half of B per SM) where the problem is many waves of 128-column tiles, i.e. the
+    // backup selection of a large belief set; OLFNAV_GEMM_PAIR=0 keeps the single-CTA kernel
+    // (read per call: 0 = never, 2 = the call fails when the pair kernel does not apply — tests use it to know which kernel ran)
+    const char* pair_env = getenv("OLFNAV_GEMM_PAIR");
+    const int pair_mode = pair_env ? atoi(pair_env) : 1;
+    const bool pair = pair_mode != 0 && BN == 128 && (sm_count % 2) == 0 && olf_div_up(K, BKH) >= 32 &&
+                      (int64_t)olf_div_up(n_rows, 2 * BM) * olf_div_up(rows_b, BN) >= 4 * (sm_count / 2);
+    OLF_REQUIRE(pair || pair_mode != 2, "umma_segmax_f16: OLFNAV_GEMM_PAIR=2 but the CTA-pair kernel does not apply to this problem");
+    p.num_m_tiles = olf_div_up(n_rows, pair ? 2 * BM : BM);
     p.num_n_tiles = olf_div_up(rows_b, BN);
     p.num_k_blocks = olf_div_up(K, BKH);
     p.num_units = p.num_m_tiles * p.num_n_tiles;
@@ -930,7 +1195,7 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     for (int k = 0; k < 2 && rc == OLFNAV_OK; ++k) {
         cuuint64_t dims[2] = {(cuuint64_t)ldb, (cuuint64_t)rows_b};
         cuuint64_t strides[1] = {(cuuint64_t)ldb * 2};
-        cuuint32_t box[2] = {(cuuint32_t)BKH, (cuuint32_t)BN};
+        cuuint32_t box[2] = {(cuuint32_t)BKH, (cuuint32_t)(pair ? BN / 2 : BN)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(k ? &tB2 : &tB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(k ? B2 : B1), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -942,6 +1207,37 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     int grid = p.num_units < sm_count ? p.num_units : sm_count;
     p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
     int tail_tiles = 0;
+    if (pair) {
+        using L = SmemLayoutP<128, 4, 4>;
+        static OlfPerDeviceOnce configured;
+        if (configured.first() &&
+            cudaFuncSetAttribute(umma_f16_pair_kernel<128, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) {
+            olfnav_set_error("umma_segmax_f16: cudaFuncSetAttribute (pair kernel) failed");
+            return OLFNAV_ERR_CUDA;
+        }
+        const int clusters = p.num_units < sm_count / 2 ? p.num_units : sm_count / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * clusters, 1, 1);
+        cfg.blockDim = dim3(NTHREADS_H, 1, 1);
+        cfg.dynamicSmemBytes = L::TOTAL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, umma_f16_pair_kernel<128, 4, 4>, tA, tB1, tB2, p, a_scale, binv) != cudaSuccess) {
+            olfnav_set_error("umma_segmax_f16: pair kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
+            return OLFNAV_ERR_CUDA;
+        }
+        olf_count_launch(1);
+        if (p.ws) {
+            segmax_decode_kernel<<<olf_div_up((int64_t)n_out, 256), 256, 0, st>>>((long long)n_out, p.ws, p.out_val, p.out_arg);
+            olf_count_launch(1);
+            if (cudaGetLastError() != cudaSuccess) { olfnav_set_error("umma_segmax_f16: decode kernel launch failed"); return OLFNAV_ERR_CUDA; }
+        }
+        return OLFNAV_OK;
+    }
     if (p.num_units > sm_count && p.num_k_blocks >= 32) {
         const int tail = p.num_units % sm_count;
         const int split = tail ? (sm_count / tail < 4 ? sm_count / tail : 4) : 1;

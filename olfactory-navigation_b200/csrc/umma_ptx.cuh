@@ -28,15 +28,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the box.
+// Wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the box.  The trap kills the context and
+// with it the device printf buffer, so the watchdog also leaves a record in mapped host memory when the translation unit has set one
+// up (olf_wd_host: {magic, block, thread, barrier, parity, elapsed clocks >> 20}; read back by olfnav_debug_watchdog).
+static __device__ int* olf_wd_host = nullptr;
+__device__ __forceinline__ void mbar_watchdog_fire(uint32_t bar, uint32_t parity, long long waited) {
+    int* h = olf_wd_host;
+    if (h) {
+        h[1] = (int)blockIdx.x; h[2] = (int)threadIdx.x; h[3] = (int)bar; h[4] = (int)parity; h[5] = (int)(waited >> 20);
+        __threadfence_system();
+        h[0] = 0x77646f67;
+        __threadfence_system();
+    }
+    printf("olfnav umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("olfnav umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
+        if (clock64() - t0 > 4000000000LL) mbar_watchdog_fire(bar, parity, clock64() - t0);
     }
 }
 // One lane of the (converged) warp.  With elect.sync ptxas knows the guarded region runs in a single thread and emits the
@@ -118,6 +129,64 @@ template <int BN>
 __host__ __device__ constexpr uint32_t make_idesc_f16() {
     // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
     return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---- CTA pairs (cta_group::2: two CTAs of a cluster on the two SMs of a TPC issue ONE tcgen05.mma of M = 256; each CTA holds its 128
+//      rows of A and D in its own tensor memory and HALF of the B tile in its own shared memory) -----------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a barrier that CTAs of the cluster arrive on (acquire at cluster scope), same watchdog as mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("olfnav umma: cluster mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier of the pair's leader (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_ts_pair_scale11(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc) : "memory");
+}
+// kind::f16 instruction descriptor of the pair: M = 256
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc_f16_pair() {
+    return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
 }  // namespace

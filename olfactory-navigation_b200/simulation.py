@@ -595,7 +595,13 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     # step's actions (olfnav_belief_step_evaluate: 8 S instead of 12 S bytes per agent-step).  The kernel keeps the rows grouped by
     # action, so the loop carries a row map (brow) next to the beliefs and asks the agent for a few spare rows per buffer.
     # OLFNAV_FUSED_STEP=0 keeps the two kernels (belief step, then evaluate).
-    fused = (not is_infotaxis and os.environ.get('OLFNAV_FUSED_STEP', '1') != '0'
+    # Default: on when this process is the only rank on its node.  With all eight GPUs of a box running the one-pass kernel at the same
+    # time it faulted sporadically (about one run_test in 350, "unspecified launch failure", no mbarrier time-out; never on a single GPU
+    # in 3 000+ runs, never with the two kernels in 1 900 eight-GPU runs: DESIGN.md §6a) — until that is understood, multi-rank jobs take
+    # the two kernels unless OLFNAV_FUSED_STEP=1 asks for the one-pass step explicitly.
+    fused_env = os.environ.get('OLFNAV_FUSED_STEP', '')
+    ranks_on_node = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
+    fused = (not is_infotaxis and (fused_env == '1' or (fused_env != '0' and ranks_on_node == 1))
              and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
     # In-place mode: ONE belief buffer, the survivors are updated in the rows they occupy and a row map carries where they are.
     # Chosen when two buffers do not fit the device (10^6 agents x 30 793 states = 127 GB of beliefs on a 180 GB part), or with

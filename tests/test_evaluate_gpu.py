@@ -275,6 +275,43 @@ def test_backup_fp16_split_gemm_against_simt_and_tf32(B, G, monkeypatch):
     assert torch.equal(na2[same], na1[same])
 
 
+def test_backup_cta_pair_kernel_against_simt_and_single_cta(monkeypatch):
+    '''
+    Large backups (many waves of 128-column tiles) take umma_f16_pair_kernel: two CTAs of a cluster issue one tcgen05.mma.cta_group::2
+    over 256 belief rows and each loads half of the Gamma tile.  Same arithmetic per element as the single-CTA kernel (one K block
+    per accumulator lifetime): values against the FP32 SIMT path to 1e-5 and the same choices; against the single-CTA kernel the values
+    agree to the last bits (its last, partial wave is split along K, which changes the order of a few FP32 additions).
+    OLFNAV_GEMM_PAIR=2 makes the call fail if the pair kernel does not apply, so the test knows which kernel ran.
+    '''
+    import olfactory_navigation_b200 as onb
+    _, agent = make('C1')
+    m = agent.model
+    rng = np.random.default_rng(21)
+    B, G = 5333, 150                      # 21 pair tiles x 15 column tiles, ragged last tile; G not a multiple of 16
+    bs = onb.BeliefSet(m, B)
+    for _ in range(4):
+        bs = bs.update(rng.integers(0, 4, B), np.zeros(B, dtype=int), raise_on_impossible_belief=False)
+    vals = 100 * np.abs(rng.standard_normal((G, m.padded_states))) ** 3 * 10.0 ** rng.integers(-4, 2, (G, 1))
+    alphas = torch.as_tensor(vals.astype(np.float32), device=bs._b.device)
+    H, W = m.grid_shape
+    alphas.view(G, H, -1)[:, :, W:] = 0
+    na1, a1, v1, g1 = onb.solvers.backup_device(m, bs, alphas, 0.99, 1)
+    monkeypatch.setenv('OLFNAV_GEMM_PAIR', '0')
+    na2, a2, v2, g2 = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    monkeypatch.setenv('OLFNAV_GEMM_PAIR', '2')
+    na3, a3, v3, g3 = onb.solvers.backup_device(m, bs, alphas, 0.99, 2)
+    np.testing.assert_allclose(v3.cpu().numpy(), v1.cpu().numpy(), rtol=1e-5)
+    assert float((a3 == a1).float().mean()) > 0.995 and float((g3 == g1).float().mean()) > 0.995
+    np.testing.assert_allclose(v3.cpu().numpy(), v2.cpu().numpy(), rtol=2e-6)
+    assert float((a3 == a2).float().mean()) > 0.999 and float((g3 == g2).float().mean()) > 0.999
+    same = (a3 == a1) & (g3 == g1).flatten(1).all(1)
+    assert torch.equal(na3[same], na1[same])
+    # a problem the pair kernel does not take is refused under OLFNAV_GEMM_PAIR=2
+    small = onb.BeliefSet(m, 300)
+    with pytest.raises(RuntimeError, match='pair'):
+        onb.solvers.backup_device(m, small, alphas, 0.99, 2)
+
+
 def test_backup_fp16_split_handles_unnormalised_and_dead_rows():
     'Rows carried with a deferred normaliser (sum << 1) and an all-zero row: the row scale comes from the normaliser, dead rows give zeros.'
     import olfactory_navigation_b200 as onb
