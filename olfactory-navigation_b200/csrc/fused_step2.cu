@@ -40,6 +40,7 @@
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 
 int olf_make_map_2d(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes, uint32_t box_rows);
 
@@ -868,6 +869,9 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
     olf_count_launch(1);
     OLF_LAUNCH_CHECK();
 
+    // diagnostics: a host that stalls between the plan kernels and the main kernel
+    static const int dbg_stall_us = [] { const char* e = getenv("OLFNAV_DEBUG_STALL_US"); return e ? atoi(e) : 0; }();
+    if (dbg_stall_us > 0) { static unsigned ctr = 0; if ((++ctr % 3) == 0) usleep((useconds_t)dbg_stall_us); }
     F2Params p;
     memset(&p, 0, sizeof(p));
     p.b_in = b_in; p.ld = ld; p.KB = g.Sp / F2_BK; p.Sp = g.Sp; p.Wp = g.Wp; p.W = g.W;

@@ -18,6 +18,7 @@ import math
 from datetime import datetime, timedelta
 
 import os
+import time
 
 import numpy as np
 import torch
@@ -548,6 +549,7 @@ def _run_batches(agent, n, start_points, time_shift, batches, **kw) -> Simulatio
 
 
 _PINNED = {}
+_DEBUG_STALL_MS = float(os.environ.get('OLFNAV_DEBUG_STALL_MS', '0') or 0)
 _SLEEP_ON_EVENTS = 2 * int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))) > (os.cpu_count() or 1)
 
 
@@ -734,6 +736,8 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
 
     def launch(i: int, n_in: int, have_act: bool) -> dict:
         'Enqueue step i for the n_in live agents of the current state (no host synchronisation).'
+        if _DEBUG_STALL_MS > 0 and (i * 2654435761 >> 7) % 3 == 0:
+            time.sleep(_DEBUG_STALL_MS * 1e-3)          # diagnostics: a host that stalls between two steps
         cur, brow_valid = S['cur'], S['brow_valid']
         r = recs[i & 1]
         if rec_free[i & 1] is not None:
