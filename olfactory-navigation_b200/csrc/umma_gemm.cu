@@ -652,9 +652,9 @@ umma_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // BN columns) lands in its own tensor memory: 48 KB per K block and SM instead of 64 (-25 % L2 traffic per flop).
 // Barriers: fullA / empty / aempty / tfull are per CTA (tcgen05.commit multicasts to both); fullB / ready / tempty live in the
 // leader and the peer's TMA engine, transform warps and epilogue warps arrive on them through the cluster address space.
-// One K block per accumulator lifetime (12 MMAs), no K split of a last partial wave (the caller only takes this kernel when there
+// Two K blocks per accumulator lifetime (24 MMAs, as in the narrow single-CTA configurations), no K split of a last partial wave (the caller only takes this kernel when there
 // are many waves).
-template <int BN, int STAGES, int TA>
+template <int BN, int STAGES, int TA, int KC>
 struct SmemLayoutP {
     static constexpr int B_HALF_BYTES = (BN / 2) * 128;
     static constexpr int STAGE_BYTES = A_TILE_BYTES_H + 2 * B_HALF_BYTES;
@@ -664,14 +664,15 @@ struct SmemLayoutP {
     static constexpr int NUM_BARS = 4 * STAGES + 4 + TA;
     static_assert(A_BASE + 64 * TA <= 512 && 2 * BN <= A_BASE, "tensor memory budget");
     static_assert(TOTAL <= 227 * 1024 && 8 * NUM_BARS + 8 <= 256, "shared memory budget");
+    static_assert(STAGES >= KC + 1 && TA >= KC, "a chunk's stages stay resident until its main pass");
 };
 
-template <int BN, int STAGES, int TA>
+template <int BN, int STAGES, int TA, int KC>
 __global__ void __launch_bounds__(NTHREADS_H, 1)
 umma_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                      const __grid_constant__ CUtensorMap tmB2, const GemmParams p, const float* __restrict__ a_scale,
                      const float* __restrict__ binv) {
-    using L = SmemLayoutP<BN, STAGES, TA>;
+    using L = SmemLayoutP<BN, STAGES, TA, KC>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -742,38 +743,58 @@ umma_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1 && leader) {
         // ===================== MMA issuer (leader only): M = 256 over both CTAs =====================
+        // KC K blocks per accumulator lifetime: the hand-over of an accumulator crosses the pair twice (commit -> peer epilogue ->
+        // remote arrive), about as long as the MMAs of one K block take; with one block per lifetime the pair ran at 1.1 us per
+        // block against 0.73 us for the single-CTA kernel.
         constexpr uint32_t idesc = make_idesc_f16_pair<BN>();
-        uint32_t it = 0;
+        uint32_t it = 0, ccount = 0;
         for (int u = cluster_id; u < p.num_units; u += n_clusters) {
-            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-                const int acc = it & 1;
-                const int s = it % STAGES;
-                mbar_wait_cluster(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
-                mbar_wait_cluster(bar_ready(s), (it / STAGES) & 1);
-                mbar_wait_cluster(bar_fullB(s), (it / STAGES) & 1);
+            for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += KC, ++ccount) {
+                const int acc = ccount & 1;
+                const int nkb = min(p.num_k_blocks - kb0, KC);
+                mbar_wait_cluster(bar_tempty(acc), ((ccount >> 1) & 1) ^ 1);
                 tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t d_tmem = tmem_base + acc * BN;
-                    const int ta = it % TA;
-                    const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta, a2 = a1 + 32;
-                    const uint64_t db1 = make_sw128_desc(b_1(s)), db2 = make_sw128_desc(b_2(s));
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                // cross terms a1.b2 + a2.b1 of the whole chunk
+                for (int j = 0; j < nkb; ++j) {
+                    const uint32_t itj = it + j;
+                    const int s = itj % STAGES;
+                    mbar_wait_cluster(bar_ready(s), (itj / STAGES) & 1);
+                    mbar_wait_cluster(bar_fullB(s), (itj / STAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a1 = tmem_base + L::A_BASE + 64 * (itj % TA), a2 = a1 + 32;
+                        const uint64_t db1 = make_sw128_desc(b_1(s)), db2 = make_sw128_desc(b_2(s));
 #pragma unroll
-                    for (int kk = 0; kk < BKH / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db2 + adv, idesc, kk > 0 ? 1u : 0u);
-                        tc_mma_f16_ts_pair(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                        for (int kk = 0; kk < BKH / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                            tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db2 + adv, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                            tc_mma_f16_ts_pair(d_tmem, a2 + kk * 8, db1 + adv, idesc, 1u);
+                        }
                     }
-#pragma unroll
-                    for (int kk = 0; kk < BKH / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 32 / 16);
-                        if (kk == 0) tc_mma_f16_ts_pair_scale11(d_tmem, a1, db1, idesc);
-                        else tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
-                    }
-                    tc_commit_pair(bar_empty(s));
-                    tc_commit_pair(bar_aempty(ta));
-                    tc_commit_pair(bar_tfull(acc));
+                    __syncwarp();
                 }
-                __syncwarp();
+                // main terms: D = a1.b1 + D * 2^-11 first, plain accumulation afterwards
+                for (int j = 0; j < nkb; ++j) {
+                    const uint32_t itj = it + j;
+                    const int s = itj % STAGES;
+                    if (elect_one_sync()) {
+                        const int ta = itj % TA;
+                        const uint32_t a1 = tmem_base + L::A_BASE + 64 * ta;
+                        const uint64_t db1 = make_sw128_desc(b_1(s));
+#pragma unroll
+                        for (int kk = 0; kk < BKH / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 32 / 16);
+                            if (j == 0 && kk == 0) tc_mma_f16_ts_pair_scale11(d_tmem, a1, db1, idesc);
+                            else tc_mma_f16_ts_pair(d_tmem, a1 + kk * 8, db1 + adv, idesc, 1u);
+                        }
+                        tc_commit_pair(bar_empty(s));
+                        tc_commit_pair(bar_aempty(ta));
+                        if (j == nkb - 1) tc_commit_pair(bar_tfull(acc));
+                    }
+                    __syncwarp();
+                }
+                it += nkb;
             }
         }
     }
@@ -845,7 +866,7 @@ umma_f16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float sum[BN];
 #pragma unroll
             for (int j = 0; j < BN; ++j) sum[j] = 0.f;
-            for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+            for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += KC, ++it) {
                 const int acc = it & 1;
                 mbar_wait(bar_tfull(acc), (it >> 1) & 1);
                 tc_fence_after();
@@ -1170,10 +1191,12 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     const int BN = rows_b <= 80 ? ((rows_b + 15) & ~15) : wide_bn;
     p.n_rows = (int)n_rows; p.K = K;
     // CTA pairs (umma_f16_pair_kernel: 256-row tiles, half of B per SM) where the problem is many waves of 128-column tiles, i.e. the
-    // backup selection of a large belief set; OLFNAV_GEMM_PAIR=0 keeps the single-CTA kernel
-    // (read per call: 0 = never, 2 = the call fails when the pair kernel does not apply — tests use it to know which kernel ran)
+    // backup selection of a large belief set
+    // OFF by default: measured 16.1 ms against 11.9 ms for the backup selection at B = 10 000, G = 512 (tensor pipe 38 % against 59 %,
+    // the pair halves B traffic but keeps the same 192 KB in flight per SM over a longer load path — latency bound).
+    // OLFNAV_GEMM_PAIR=1 takes it where it applies, =2 makes the call fail when it does not (tests use it to know which kernel ran).
     const char* pair_env = getenv("OLFNAV_GEMM_PAIR");
-    const int pair_mode = pair_env ? atoi(pair_env) : 1;
+    const int pair_mode = pair_env ? atoi(pair_env) : 0;
     const bool pair = pair_mode != 0 && BN == 128 && (sm_count % 2) == 0 && olf_div_up(K, BKH) >= 32 &&
                       (int64_t)olf_div_up(n_rows, 2 * BM) * olf_div_up(rows_b, BN) >= 4 * (sm_count / 2);
     OLF_REQUIRE(pair || pair_mode != 2, "umma_segmax_f16: OLFNAV_GEMM_PAIR=2 but the CTA-pair kernel does not apply to this problem");
@@ -1208,10 +1231,10 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
     p.full_units = p.num_units; p.tail_split = 1; p.tail_ws = nullptr;
     int tail_tiles = 0;
     if (pair) {
-        using L = SmemLayoutP<128, 4, 4>;
+        using L = SmemLayoutP<128, 4, 4, 2>;
         static OlfPerDeviceOnce configured;
         if (configured.first() &&
-            cudaFuncSetAttribute(umma_f16_pair_kernel<128, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) {
+            cudaFuncSetAttribute(umma_f16_pair_kernel<128, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) {
             olfnav_set_error("umma_segmax_f16: cudaFuncSetAttribute (pair kernel) failed");
             return OLFNAV_ERR_CUDA;
         }
@@ -1226,7 +1249,7 @@ int olf_umma_segmax_f16(const float* A, int64_t lda, int64_t n_rows, int K, cons
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, umma_f16_pair_kernel<128, 4, 4>, tA, tB1, tB2, p, a_scale, binv) != cudaSuccess) {
+        if (cudaLaunchKernelEx(&cfg, umma_f16_pair_kernel<128, 4, 4, 2>, tA, tB1, tB2, p, a_scale, binv) != cudaSuccess) {
             olfnav_set_error("umma_segmax_f16: pair kernel launch failed (%s)", cudaGetErrorString(cudaGetLastError()));
             return OLFNAV_ERR_CUDA;
         }

@@ -277,10 +277,9 @@ def test_backup_fp16_split_gemm_against_simt_and_tf32(B, G, monkeypatch):
 
 def test_backup_cta_pair_kernel_against_simt_and_single_cta(monkeypatch):
     '''
-    Large backups (many waves of 128-column tiles) take umma_f16_pair_kernel: two CTAs of a cluster issue one tcgen05.mma.cta_group::2
-    over 256 belief rows and each loads half of the Gamma tile.  Same arithmetic per element as the single-CTA kernel (one K block
-    per accumulator lifetime): values against the FP32 SIMT path to 1e-5 and the same choices; against the single-CTA kernel the values
-    agree to the last bits (its last, partial wave is split along K, which changes the order of a few FP32 additions).
+    umma_f16_pair_kernel (opt-in, OLFNAV_GEMM_PAIR=1): two CTAs of a cluster issue one tcgen05.mma.cta_group::2 over 256 belief rows and
+    each loads half of the Gamma tile.  Same split scheme as the single-CTA kernel (two K blocks per accumulator lifetime instead of
+    one): values against the FP32 SIMT path to 1e-5 and the same choices; against the single-CTA kernel to 2e-6.
     OLFNAV_GEMM_PAIR=2 makes the call fail if the pair kernel does not apply, so the test knows which kernel ran.
     '''
     import olfactory_navigation_b200 as onb
