@@ -308,11 +308,6 @@ typedef struct olfnav_sim_step_args {
     void* ev_plan_done;
 } olfnav_sim_step_args;
 
-/* Diagnostics: out[8]; out[0] != 0 when an mbarrier wait of the one-pass step kernel timed out in this process (the kernel traps, which
- * is reported as a launch failure): out[1..5] = block, thread, barrier address, parity, waited clocks >> 20.  Host memory: readable
- * after the CUDA context has died. */
-int olfnav_debug_watchdog(int32_t* out /* [host] 8 ints */);
-
 int olfnav_sim_step(const olfnav_model* m, const olfnav_alphas* alphas /* NULL = infotaxis */, const olfnav_env* e,
                     const olfnav_sim_step_args* args /* [host] */, void* stream);
 

@@ -52,7 +52,6 @@ SIGNATURES = {
     'olfnav_evaluate': (_i, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i, _p]),
     'olfnav_infotaxis_choose': (_i, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     'olfnav_infotaxis_last_unsure': (_i, [_p, ctypes.POINTER(ctypes.c_int32), _p]),
-    'olfnav_debug_watchdog': (_i, [ctypes.POINTER(ctypes.c_int32)]),
     'olfnav_entropies': (_i, [_p, _p, _i64, _i64, _p, _p, _p]),
     'olfnav_backup_gamma': (_i, [_p, _p, _i64, _i, _f, _p, _i64, _p]),
     'olfnav_backup_select': (_i, [_p, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p, _p, _i, _p]),

@@ -28,26 +28,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the box.  The trap kills the context and
-// with it the device printf buffer, so the watchdog also leaves a record in mapped host memory when the translation unit has set one
-// up (olf_wd_host: {magic, block, thread, barrier, parity, elapsed clocks >> 20}; read back by olfnav_debug_watchdog).
-static __device__ int* olf_wd_host = nullptr;
-__device__ __forceinline__ void mbar_watchdog_fire(uint32_t bar, uint32_t parity, long long waited) {
-    int* h = olf_wd_host;
-    if (h) {
-        h[1] = (int)blockIdx.x; h[2] = (int)threadIdx.x; h[3] = (int)bar; h[4] = (int)parity; h[5] = (int)(waited >> 20);
-        __threadfence_system();
-        h[0] = 0x77646f67;
-        __threadfence_system();
-    }
-    printf("olfnav umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-    __trap();
-}
+// Wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging the box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) mbar_watchdog_fire(bar, parity, clock64() - t0);
+        if (clock64() - t0 > 4000000000LL) {
+            printf("olfnav umma: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
     }
 }
 // One lane of the (converged) warp.  With elect.sync ptxas knows the guarded region runs in a single thread and emits the

@@ -553,6 +553,22 @@ _DEBUG_STALL_MS = float(os.environ.get('OLFNAV_DEBUG_STALL_MS', '0') or 0)
 _SLEEP_ON_EVENTS = 2 * int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))) > (os.cpu_count() or 1)
 
 
+def _host_busy_fraction(window_s: float = 0.03) -> float:
+    'Fraction of the host cores that were busy over a short window (/proc/stat; 0 where that is not available).'
+    def snap():
+        with open('/proc/stat') as f:
+            v = [float(x) for x in f.readline().split()[1:]]
+        idle = v[3] + (v[4] if len(v) > 4 else 0.0)
+        return sum(v), idle
+    try:
+        t0, i0 = snap()
+        time.sleep(window_s)
+        t1, i1 = snap()
+        return 0.0 if t1 <= t0 else max(0.0, 1.0 - (i1 - i0) / (t1 - t0))
+    except Exception:
+        return 0.0
+
+
 def _pinned(name: str, nbytes: int) -> torch.Tensor:
     '''
     Page-locked host staging buffers are kept across run_test calls (grown on demand): cudaHostAlloc of a few MB costs milliseconds,
@@ -597,14 +613,17 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     # step's actions (olfnav_belief_step_evaluate: 8 S instead of 12 S bytes per agent-step).  The kernel keeps the rows grouped by
     # action, so the loop carries a row map (brow) next to the beliefs and asks the agent for a few spare rows per buffer.
     # OLFNAV_FUSED_STEP=0 keeps the two kernels (belief step, then evaluate).
-    # Default: on when this process is the only rank on its node.  With all eight GPUs of a box running the one-pass kernel at the same
-    # time it faulted sporadically (about one run_test in 350, "unspecified launch failure", no mbarrier time-out; never on a single GPU
-    # in 3 000+ runs, never with the two kernels in 1 900 eight-GPU runs: DESIGN.md §6a) — until that is understood, multi-rank jobs take
-    # the two kernels unless OLFNAV_FUSED_STEP=1 asks for the one-pass step explicitly.
+    # Default: on when this process is the only rank on its node AND the host is not saturated.  The kernel has an open fault
+    # (csrc/fused_step2.cu store issuer): a hardware exception once in a few hundred run_test calls when all eight GPUs
+    # of a box run it or every host core is busy, never on a quiet single-GPU box in 3 000+ calls, never with the two kernels in 1 900
+    # eight-GPU runs.  Until that is understood, multi-rank jobs and busy hosts take the two kernels; OLFNAV_FUSED_STEP=1 forces the
+    # one-pass step (with OLFNAV_F2_STORE_SYNC=1 the kernel waits for its stores after every block: no fault seen, 15 % slower),
+    # OLFNAV_FUSED_STEP=0 forbids it.
     fused_env = os.environ.get('OLFNAV_FUSED_STEP', '')
     ranks_on_node = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
-    fused = (not is_infotaxis and (fused_env == '1' or (fused_env != '0' and ranks_on_node == 1))
-             and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1)
+    fused = not is_infotaxis and fused_env != '0' and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1
+    if fused and fused_env != '1':
+        fused = ranks_on_node == 1 and _host_busy_fraction() < 0.5
     # In-place mode: ONE belief buffer, the survivors are updated in the rows they occupy and a row map carries where they are.
     # Chosen when two buffers do not fit the device (10^6 agents x 30 793 states = 127 GB of beliefs on a 180 GB part), or with
     # OLFNAV_INPLACE=1; it takes the two-kernel step (the one-pass kernel writes the rows somewhere else by construction) and the
