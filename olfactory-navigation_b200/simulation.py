@@ -553,18 +553,30 @@ _DEBUG_STALL_MS = float(os.environ.get('OLFNAV_DEBUG_STALL_MS', '0') or 0)
 _SLEEP_ON_EVENTS = 2 * int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))) > (os.cpu_count() or 1)
 
 
+_BUSY_STATE = {'snap': None, 'value': 0.0}
+
+
 def _host_busy_fraction(window_s: float = 0.03) -> float:
-    'Fraction of the host cores that were busy over a short window (/proc/stat; 0 where that is not available).'
+    '''
+    Fraction of the host cores that were busy recently (/proc/stat; 0 where that is not available).  The first call in a process
+    measures over a short window; later calls use the interval since the previous call, so that a run_test call does not pay for it.
+    '''
     def snap():
         with open('/proc/stat') as f:
             v = [float(x) for x in f.readline().split()[1:]]
-        idle = v[3] + (v[4] if len(v) > 4 else 0.0)
-        return sum(v), idle
+        return sum(v), v[3] + (v[4] if len(v) > 4 else 0.0)
     try:
-        t0, i0 = snap()
-        time.sleep(window_s)
-        t1, i1 = snap()
-        return 0.0 if t1 <= t0 else max(0.0, 1.0 - (i1 - i0) / (t1 - t0))
+        now = snap()
+        prev = _BUSY_STATE['snap']
+        if prev is None:
+            time.sleep(window_s)
+            prev, now = now, snap()
+        if now[0] - prev[0] >= 16:                       # a meaningful number of clock ticks
+            _BUSY_STATE['value'] = max(0.0, 1.0 - (now[1] - prev[1]) / (now[0] - prev[0]))
+            _BUSY_STATE['snap'] = now
+        elif _BUSY_STATE['snap'] is None:
+            _BUSY_STATE['snap'] = prev
+        return _BUSY_STATE['value']
     except Exception:
         return 0.0
 

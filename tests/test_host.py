@@ -184,3 +184,19 @@ def test_generic_loop_records_the_odor_cue_of_space_aware_agents():
         assert np.array_equal(hist.positions[step][live], seen[:, 1:].astype(int))
         live = live[hist.done_at_step[live] != step + 1]
     assert len(hist.simulation_dfs) == n
+
+
+def test_host_busy_probe_is_cheap_and_bounded():
+    '''
+    run_test only takes the one-pass step kernel on quiet single-rank hosts: the probe behind that decision returns a
+    fraction in [0, 1] and costs nothing after its first call in a process.
+    '''
+    import time
+    from olfactory_navigation_b200 import simulation as sim
+    v = sim._host_busy_fraction()
+    assert 0.0 <= v <= 1.0
+    t = time.perf_counter()
+    for _ in range(20):
+        w = sim._host_busy_fraction()
+        assert 0.0 <= w <= 1.0
+    assert time.perf_counter() - t < 0.02
