@@ -55,6 +55,7 @@ constexpr int F2_BOX = BM * 128;           // bytes of one 32-float box of 128 r
 constexpr int F2_A_BYTES = 2 * F2_BOX;     // raw / updated tile of a K block: 128 rows x 64 floats
 constexpr int F2_MAX_O = 6;                // likelihood slices staged per K block
 constexpr int F2_TAB_BYTES = (F2_MAX_O + 2) * F2_BK * 4;
+constexpr int F2_STORE_MODE = 0;           // see F2Params::store_mode (run_test sets OLFNAV_F2_STORE_MODE=1 when it is forced onto a busy host)
 constexpr int F2_STORE_SYNC = 0;           // 1: the store thread waits for the FULL completion of its TMA stores after every K block (safe, -15 %)
 constexpr int F2_RING = 8;                 // per-block A scales in flight between the transform and the epilogue
 constexpr int F2_MAX_BN = 80;
@@ -63,6 +64,9 @@ constexpr int F2_PLAN_ITEMS = 4096;        // agents per CTA of the plan kernels
 struct F2Params {
     const float* b_in; long long ld;
     int KB, Sp, Wp, W;
+    int store_mode;                        // 1: every transform warp stores its own 32 rows of a block and waits for the FULL completion of that
+                                           // store before it releases the stage (OLFNAV_F2_STORE_MODE; 0: one store thread, release after the
+                                           // shared-memory read: the open fault of DESIGN §6a)
     int store_sync;                        // full completion wait of the TMA stores every store_sync-th K block (OLFNAV_F2_STORE_SYNC, 0 = never)
     int dbg;                               // OLFNAV_F2_DBG ablation bits: 1 no stores, 2 no MMAs, 4 no tensor-memory writes, 8 no update arithmetic,
                                            // 32 no alpha-plane loads (8 + 32 + 2 or 4: the mode that reproduced the store fault in every run)
@@ -213,7 +217,7 @@ __device__ __forceinline__ void f2_update(uint8_t* rowp, int sw, const float* li
 
 template <int BN>
 __global__ void __launch_bounds__(F2_THREADS, 1)
-fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut32,
               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ F2Params p) {
     using L = F2Layout<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -237,7 +241,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     constexpr uint32_t TMEM_COLS = 512;
 
     if (warp == 3 && lane == 0) {
-        for (int s = 0; s < F2_STAGES; ++s) { mbar_init(bar_fullA(s), 2); mbar_init(bar_ready(s), 4); mbar_init(bar_emptyA(s), 1); }
+        for (int s = 0; s < F2_STAGES; ++s) { mbar_init(bar_fullA(s), 2); mbar_init(bar_ready(s), 4); mbar_init(bar_emptyA(s), p.store_mode ? 4 : 1); }
         for (int s = 0; s < F2_BSTAGES; ++s) { mbar_init(bar_fullB(s), 1); mbar_init(bar_emptyB(s), 1); }
         for (int t = 0; t < F2_TA; ++t) mbar_init(bar_aempty(t), 1);
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 4); }
@@ -247,6 +251,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmIn) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmOut) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmOut32) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB1) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB2) : "memory");
     }
@@ -387,8 +392,8 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
               }
             }
         } else {
-            // ===================== store issuer: updated tile -> 128 consecutive rows of b_out =====================
-            if (elect_one_sync()) {
+            // ===================== store issuer: updated tile -> 128 consecutive rows of b_out (store_mode 0) =====================
+            if (!p.store_mode && elect_one_sync()) {
                 uint32_t it = 0;
                 for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
                     int tile, kb0, nblk;
@@ -412,10 +417,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                         // ("unspecified launch failure"): once in a few hundred run_test calls when all eight GPUs of a box run this
                         // kernel or the host is saturated, never in 3 000+ calls on a quiet single-GPU box, and in EVERY run of the
                         // ablation mode that removes the arithmetic and the plane loads (OLFNAV_F2_DBG=46).  Without the stores
-                        // (OLFNAV_F2_DBG bit 1) it never happens.  Waiting for the FULL completion of the stores after every K block
-                        // (store_sync = 1, OLFNAV_F2_STORE_SYNC=1) removes it — 0 faults in 27 ablation runs — and costs 15 % of the
-                        // kernel (0.76 ms of 5.1), whatever number of groups is allowed to stay pending; a full wait every 4th or 8th
-                        // block does not help.  run_test therefore keeps this kernel for quiet single-rank hosts (simulation.py).
+                        // (OLFNAV_F2_DBG bit 1) it never happens.  Waiting for the FULL completion of the stores before the stage is
+                        // released removes it: store_sync = 1 (this thread waits after every block: 0 faults in 27 ablation runs,
+                        // 5.85 ms instead of 5.1) or store_mode = 1 (the transform warps store their own rows and wait: 0 faults,
+                        // 5.3-5.5 ms, rows still bit-identical); a full wait every 4th or 8th block does not help.  run_test keeps
+                        // this fast path for quiet single-rank hosts (simulation.py) and takes store_mode 1 when it is forced elsewhere.
                         if (p.store_sync > 0 && (int)(it % (uint32_t)p.store_sync) == p.store_sync - 1)
                             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     }
@@ -542,6 +548,21 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_ready(s));
+                if (p.store_mode) {
+                    // this warp's 32 rows of the block go out now; the stage is released when the store has COMPLETED (not merely read
+                    // shared memory: DESIGN §6a) — the wait falls into the half block period this warp would idle anyway
+                    if (elect_one_sync()) {
+                        if (!(p.dbg & 1)) {
+                            const uint32_t srcw = base + s * L::STAGE + (uint32_t)(warp & 3) * 32 * 128;
+                            f2_store_2d(&tmOut32, srcw, kb * F2_BK, tile * BM + (warp & 3) * 32);
+                            f2_store_2d(&tmOut32, srcw + F2_BOX, kb * F2_BK + 32, tile * BM + (warp & 3) * 32);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        mbar_arrive(bar_emptyA(s));
+                    }
+                    __syncwarp();
+                }
             }
             it = it_seg + nblk;
             // normaliser share of this segment (both groups write theirs; the finishing kernel adds them in a fixed order)
@@ -785,13 +806,13 @@ int f2_encode(CUtensorMap* map, CUtensorMapDataType dt, const void* ptr, uint64_
 }
 
 template <int BN>
-int f2_launch(const CUtensorMap& tIn, const CUtensorMap& tOut, const CUtensorMap& tB1, const CUtensorMap& tB2, const F2Params& p, int grid,
-              cudaStream_t st) {
+int f2_launch(const CUtensorMap& tIn, const CUtensorMap& tOut, const CUtensorMap& tOut32, const CUtensorMap& tB1, const CUtensorMap& tB2,
+              const F2Params& p, int grid, cudaStream_t st) {
     using L = F2Layout<BN>;
     static OlfPerDeviceOnce configured;
     if (configured.first())
         OLF_CUDA(cudaFuncSetAttribute(fused2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    fused2_kernel<BN><<<grid, F2_THREADS, L::TOTAL, st>>>(tIn, tOut, tB1, tB2, p);
+    fused2_kernel<BN><<<grid, F2_THREADS, L::TOTAL, st>>>(tIn, tOut, tOut32, tB1, tB2, p);
     OLF_LAUNCH_CHECK();
     return OLFNAV_OK;
 }
@@ -869,24 +890,26 @@ int olf_fused_step_launch(const olfnav_model* m, const olfnav_alphas* a, const f
     memset(&p, 0, sizeof(p));
     p.b_in = b_in; p.ld = ld; p.KB = g.Sp / F2_BK; p.Sp = g.Sp; p.Wp = g.Wp; p.W = g.W;
     { const char* e = getenv("OLFNAV_F2_DBG"); p.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("OLFNAV_F2_STORE_MODE"); p.store_mode = e ? (atoi(e) != 0) : F2_STORE_MODE; }
     { const char* e = getenv("OLFNAV_F2_STORE_SYNC"); p.store_sync = e ? atoi(e) : F2_STORE_SYNC; if (p.store_sync < 0) p.store_sync = 0; }
     p.n_tiles_max = n_tiles_max; p.n_tiles_dev = n_tiles_dev; p.tile_act = tile_act; p.slot_src = slot_src; p.slot_obs = slot_obs;
     p.scale_in = scale_in; p.obs_tab = m->obs; p.coef = m->coef; p.A = g.A; p.O = g.O; p.obs_per_action = g.obs_per_action;
     for (int k = 0; k < g.A; ++k) { p.dy[k] = g.moves[k][0]; p.dx[k] = g.moves[k][1]; }
     p.ws_sum = s_sum.as<float>(); p.ws_z = s_z.as<float>(); p.binv = a->binv;
 
-    CUtensorMap tIn, tOut, tB1, tB2;
+    CUtensorMap tIn, tOut, tOut32, tB1, tB2;
     int rc = f2_encode(&tIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_in, (uint64_t)g.Sp, (uint64_t)rows_in, (uint64_t)ld * 4, 32, 1, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc == OLFNAV_OK) rc = f2_encode(&tOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_out, (uint64_t)g.Sp, (uint64_t)rows_out, (uint64_t)ld * 4, 32, BM, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc == OLFNAV_OK) rc = f2_encode(&tOut32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_out, (uint64_t)g.Sp, (uint64_t)rows_out, (uint64_t)ld * 4, 32, 32, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc == OLFNAV_OK) rc = f2_encode(&tB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a->h1, (uint64_t)a->ldh, (uint64_t)a->Gp, (uint64_t)a->ldh * 2, F2_BK, (uint32_t)BN, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc == OLFNAV_OK) rc = f2_encode(&tB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a->h2, (uint64_t)a->ldh, (uint64_t)a->Gp, (uint64_t)a->ldh * 2, F2_BK, (uint32_t)BN, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc != OLFNAV_OK) return rc;
     switch (BN) {
-        case 16: rc = f2_launch<16>(tIn, tOut, tB1, tB2, p, grid, st); break;
-        case 32: rc = f2_launch<32>(tIn, tOut, tB1, tB2, p, grid, st); break;
-        case 48: rc = f2_launch<48>(tIn, tOut, tB1, tB2, p, grid, st); break;
-        case 64: rc = f2_launch<64>(tIn, tOut, tB1, tB2, p, grid, st); break;
-        default: rc = f2_launch<80>(tIn, tOut, tB1, tB2, p, grid, st); break;
+        case 16: rc = f2_launch<16>(tIn, tOut, tOut32, tB1, tB2, p, grid, st); break;
+        case 32: rc = f2_launch<32>(tIn, tOut, tOut32, tB1, tB2, p, grid, st); break;
+        case 48: rc = f2_launch<48>(tIn, tOut, tOut32, tB1, tB2, p, grid, st); break;
+        case 64: rc = f2_launch<64>(tIn, tOut, tOut32, tB1, tB2, p, grid, st); break;
+        default: rc = f2_launch<80>(tIn, tOut, tOut32, tB1, tB2, p, grid, st); break;
     }
     if (rc != OLFNAV_OK) return rc;
     fused2_finish_kernel<<<n_tiles_max, BM, 0, st>>>(BN, a->G, p.KB, grid, n_tiles_max, n_tiles_dev, slot_src, slot_id, p.ws_sum, p.ws_z, a->actions,

@@ -629,13 +629,18 @@ def _run_single(agent, n, start_points, time_shift, environment, time_loop, hori
     # (csrc/fused_step2.cu store issuer): a hardware exception once in a few hundred run_test calls when all eight GPUs
     # of a box run it or every host core is busy, never on a quiet single-GPU box in 3 000+ calls, never with the two kernels in 1 900
     # eight-GPU runs.  Until that is understood, multi-rank jobs and busy hosts take the two kernels; OLFNAV_FUSED_STEP=1 forces the
-    # one-pass step (with OLFNAV_F2_STORE_SYNC=1 the kernel waits for its stores after every block: no fault seen, 15 % slower),
-    # OLFNAV_FUSED_STEP=0 forbids it.
+    # one-pass step, OLFNAV_FUSED_STEP=0 forbids it.
     fused_env = os.environ.get('OLFNAV_FUSED_STEP', '')
     ranks_on_node = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
     fused = not is_infotaxis and fused_env != '0' and lib.olfnav_can_fuse_policy(model_h, alphas_h) == 1
-    if fused and fused_env != '1':
-        fused = ranks_on_node == 1 and _host_busy_fraction() < 0.5
+    if fused:
+        quiet = ranks_on_node == 1 and _host_busy_fraction() < 0.5
+        if fused_env != '1':
+            fused = quiet
+        elif not quiet:
+            # forced onto a busy or multi-rank host: the kernel variant whose stores complete before a stage is released (no fault
+            # seen, 12 % slower; the library reads the variable at every launch)
+            os.environ.setdefault('OLFNAV_F2_STORE_MODE', '1')
     # In-place mode: ONE belief buffer, the survivors are updated in the rows they occupy and a row map carries where they are.
     # Chosen when two buffers do not fit the device (10^6 agents x 30 793 states = 127 GB of beliefs on a 180 GB part), or with
     # OLFNAV_INPLACE=1; it takes the two-kernel step (the one-pass kernel writes the rows somewhere else by construction) and the

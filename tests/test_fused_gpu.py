@@ -135,6 +135,30 @@ def test_fused_matches_separate_calls(cfg, G):
     assert clear.mean() > 0.9
 
 
+@pytest.mark.parametrize('cfg', ['T1p', 'wide', 'diag', 'C2'])
+@pytest.mark.parametrize('mode', ['store_mode', 'store_sync'])
+def test_safe_store_variants_write_the_same_rows(cfg, mode, monkeypatch):
+    '''
+    The two variants of the kernel that wait for the FULL completion of their TMA stores before a shared-memory stage is reused
+    (OLFNAV_F2_STORE_MODE=1: the transform warps store their own 32 rows; OLFNAV_F2_STORE_SYNC=1: the store thread waits after every
+    block; DESIGN §6a: the cure of the kernel's open fault) against the two separate calls: same bar as the default kernel.
+    '''
+    import olfactory_navigation_b200 as onb
+    monkeypatch.setenv('OLFNAV_F2_STORE_MODE' if mode == 'store_mode' else 'OLFNAV_F2_STORE_SYNC', '1')
+    agent = fusable(cfg)
+    m = agent.model
+    n, G = 700, 75
+    B, act, obs, alphas, alpha_actions = _random_inputs(m, n, G, seed=11)
+    vf = onb.ValueFunction(m, alphas, alpha_actions)
+    assert _is_fused(m, vf)
+    bs = onb.BeliefSet(m, B)
+    ref = _separate(onb, m, vf, bs, act, obs)
+    new, ok, val, arg, action = bs.update_and_evaluate(vf, act, obs)
+    rows, good = _compare(new, ok, val, arg, action, ref, alpha_actions)
+    sc = rows @ alphas.T
+    np.testing.assert_allclose(val.cpu().numpy()[good], sc.max(1), rtol=1e-5)
+
+
 @pytest.mark.parametrize('cfg', ['T1p', 'wide', 'diag', 'T0', 'T2'])
 def test_fused_against_oracle(cfg):
     import olfactory_navigation_b200 as onb
