@@ -38,6 +38,17 @@ def run_test_sharded(agent, n: int, start_points: np.ndarray, time_shift: np.nda
     from .simulation import run_test
     rank, ws = world()
     lo, hi = shard_bounds(n, rank, ws)
+    env = kwargs.get('environment', None)
+    if env is None:
+        env = getattr(agent, 'environment', None)
+    if ws > 1 and rank == 0 and getattr(env, 'reference_time_quirk', False) and len(np.unique(np.asarray(time_shift))) > 1:
+        # Under the reference's sorted-time indexing (environment.py:598-601, reproduced by default) agent i observes the frame of the
+        # i-th smallest time AMONG THE AGENTS OF ITS BATCH: a shard is a batch of its own, so a sharded run is a valid run of the
+        # reference's loop per shard but not the same trajectories as one batch over all agents.
+        import warnings
+        warnings.warn('run_test_sharded: Environment.reference_time_quirk is on and the time shifts differ between agents: every shard '
+                      'observes by its own sorted-time order, results are not comparable with a single-batch run '
+                      '(set environment.reference_time_quirk = False for shard-invariant trajectories)', stacklevel=2)
     kwargs.setdefault('print_progress', False)
     kwargs.setdefault('print_stats', False)
     hist = run_test(agent, n=hi - lo, start_points=np.asarray(start_points)[lo:hi], time_shift=np.asarray(time_shift)[lo:hi], **kwargs) if hi > lo else None
