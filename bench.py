@@ -403,6 +403,8 @@ def run_ours(args) -> None:
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'{args.config} {label}: ' + WORKLOADS[CONFIG],
                        'agents_per_gpu': n, 'alpha_vectors': G, 'evaluate_path': evaluate_path, 'one_pass_step': bool(fused), 'step_mode': step_mode,
+                       'step_mode_note': ('multi-rank jobs take the two-kernel step by default: the one-pass kernel (N = 1 default, 4.8 ms/step) has an open '
+                                          'fault on fully loaded 8-GPU boxes (DESIGN.md 6a); OLFNAV_FUSED_STEP=1 forces it') if (world > 1 and not fused) else None,
                        'sharding': 'agents split across ranks, no data-path collective',
                        'layout': 'grid rows padded to %d floats (%d padded states for %d states)' % (model.padded_width, Sp, S),
                        'l2': 'belief buffers (2 x %.1f GB) far exceed the 126 MB L2' % (n * Sp * 4 / 1e9)},
