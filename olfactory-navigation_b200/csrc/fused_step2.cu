@@ -67,7 +67,8 @@ struct F2Params {
     int store_mode;                        // 1: every transform warp stores its own 32 rows of a block and waits for the FULL completion of that
                                            // store before it releases the stage (OLFNAV_F2_STORE_MODE; 0: one store thread, release after the
                                            // shared-memory read: the open fault of DESIGN §6a)
-    int store_sync;                        // full completion wait of the TMA stores every store_sync-th K block (OLFNAV_F2_STORE_SYNC, 0 = never)
+    int store_sync;                        // OLFNAV_F2_STORE_SYNC: 0 release after the .read wait (fast, the open fault), 1 full completion wait after every
+                                           // block, 2 release one block later, after the full completion of the stores (deferred)
     int dbg;                               // OLFNAV_F2_DBG ablation bits: 1 no stores, 2 no MMAs, 4 no tensor-memory writes, 8 no update arithmetic,
                                            // 32 no alpha-plane loads (8 + 32 + 2 or 4: the mode that reproduced the store fault in every run)
     int n_tiles_max; const int* n_tiles_dev;
@@ -394,6 +395,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
         } else {
             // ===================== store issuer: updated tile -> 128 consecutive rows of b_out (store_mode 0) =====================
             if (!p.store_mode && elect_one_sync()) {
+                // store_sync = 2: a stage is released one block LATER, when the next block is ready to be stored and the stores of this one
+                // have had a whole block period to complete — the full-completion wait then finds nothing to wait for, at most one
+                // block's stores are ever outstanding, and the price is one stage of ring depth instead of a stall
+                const bool deferred = p.store_sync == 2;
+                int prev_s = -1;
                 uint32_t it = 0;
                 for (int u = blockIdx.x; u < Wk.num_units; u += gridDim.x) {
                     int tile, kb0, nblk;
@@ -402,6 +408,10 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                     for (int j = 0; j < nblk; ++j, ++it) {
                         const int s = it % F2_STAGES;
                         mbar_wait(bar_ready(s), (it / F2_STAGES) & 1);
+                        if (deferred && prev_s >= 0) {
+                            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                            mbar_arrive(bar_emptyA(prev_s));
+                        }
                         const uint32_t src = base + s * L::STAGE;
                         if (!(p.dbg & 1)) {
                             const int k0 = kb_at(sdx, kb0, nblk, j) * F2_BK;
@@ -411,6 +421,7 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         // the stage goes back to the producers as soon as the stores have read it (a store read takes a fraction of
                         // a block period; waiting for the next block's commit first would hold every stage one period longer)
+                        if (deferred) { prev_s = s; continue; }
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         mbar_arrive(bar_emptyA(s));
                         // OPEN FAULT.  Releasing the stage after the .read wait alone ends, rarely, in a hardware exception
@@ -422,11 +433,11 @@ fused2_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ 
                         // 5.85 ms instead of 5.1) or store_mode = 1 (the transform warps store their own rows and wait: 0 faults,
                         // 5.3-5.5 ms, rows still bit-identical); a full wait every 4th or 8th block does not help.  run_test keeps
                         // this fast path for quiet single-rank hosts (simulation.py) and takes store_mode 1 when it is forced elsewhere.
-                        if (p.store_sync > 0 && (int)(it % (uint32_t)p.store_sync) == p.store_sync - 1)
-                            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        if (p.store_sync == 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     }
                 }
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                if (deferred && prev_s >= 0) mbar_arrive(bar_emptyA(prev_s));
             }
         }
     } else if (warp < 12) {

@@ -136,15 +136,16 @@ def test_fused_matches_separate_calls(cfg, G):
 
 
 @pytest.mark.parametrize('cfg', ['T1p', 'wide', 'diag', 'C2'])
-@pytest.mark.parametrize('mode', ['store_mode', 'store_sync'])
+@pytest.mark.parametrize('mode', ['store_mode', 'store_sync', 'deferred'])
 def test_safe_store_variants_write_the_same_rows(cfg, mode, monkeypatch):
     '''
-    The two variants of the kernel that wait for the FULL completion of their TMA stores before a shared-memory stage is reused
+    The variants of the kernel that wait for the FULL completion of their TMA stores before a shared-memory stage is reused
     (OLFNAV_F2_STORE_MODE=1: the transform warps store their own 32 rows; OLFNAV_F2_STORE_SYNC=1: the store thread waits after every
-    block; DESIGN §6a: the cure of the kernel's open fault) against the two separate calls: same bar as the default kernel.
+    block; =2: it releases a stage one block later; DESIGN §6a: the cures of the kernel's open fault) against the two separate calls:
+    same bar as the default kernel.
     '''
     import olfactory_navigation_b200 as onb
-    monkeypatch.setenv('OLFNAV_F2_STORE_MODE' if mode == 'store_mode' else 'OLFNAV_F2_STORE_SYNC', '1')
+    monkeypatch.setenv('OLFNAV_F2_STORE_MODE' if mode == 'store_mode' else 'OLFNAV_F2_STORE_SYNC', '2' if mode == 'deferred' else '1')
     agent = fusable(cfg)
     m = agent.model
     n, G = 700, 75
