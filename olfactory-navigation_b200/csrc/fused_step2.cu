@@ -16,9 +16,11 @@
 //     agent's belief now lives is handed back to the caller (row_out).
 //   * HBM takes 256-byte row segments at 5.9 TB/s only when they are line aligned (4.8 TB/s at a 16-byte offset): grid rows are
 //     padded to 64 floats (olfnav_padded_width_for), which also makes the state space a whole number of 64-state K blocks.
-//   * work is cut stream-K: the CTAs split the sequence of (tile, K block) pairs evenly, so 785 tiles on 148 SMs cost 5.3 waves,
-//     not 6.  Every (CTA, tile) segment writes FP32 partial sums; fused2_finish_kernel adds them in CTA order (deterministic),
-//     takes the first argmax and the normaliser, and writes scale / ok / action per agent.
+//   * work = whole tiles, the CTAs of a wave walking their K blocks in lockstep (they touch the same K range of the tables together), and
+//     the tiles of the last, partial wave cut along K into up to 8 parts so that the wave covers all SMs (785 tiles on 148 SMs cost
+//     5.3 waves, not 6; a stream-K split of the whole (tile, K block) sequence measured the same and was dropped).  Every unit writes
+//     FP32 partial sums; fused2_finish_kernel adds them in unit order (deterministic), takes the first argmax and the normaliser, and
+//     writes scale / ok / action per agent.
 //
 // Numerics: the row is b' = (w·scale_in)·O with w = cA·b(s'-δ) + cB·b(s'-dy·Wp) (cA, cB 0/1 masks of the x move: bit-identical
 // to belief_step_tma_kernel).  The GEMM is the 2-way FP16 split of umma_f16_kernel with ONE change: the power-of-two scale of the
@@ -28,11 +30,18 @@
 // Warp groups (512 threads, one CTA per SM; setmaxnreg moves registers from WG0 to the others — the pool is what the CTA was
 // launched with, 512 x 128):
 //   WG0  warp 0  producer: rows 0-63 of the tile (TMA gather4) + the table slices of the block
-//        warp 1  producer: the alpha planes of the block + rows 64-127 of the tile
-//        warp 2  TMEM allocation, MMA issuer          warp 3  store issuer
+//        warp 1  producer: rows 64-127 of the tile
+//        warp 2  TMEM allocation, MMA issuer, loader of the alpha planes (two-deep ring, one block ahead)
+//        warp 3  store issuer (TMA tensor stores of the updated block; see the store modes below)
 //   WG1  warps 4-7    update + A transform of the even K blocks (thread = row = TMEM lane)
 //   WG2  warps 8-11   ... of the odd K blocks
-//   WG3  warps 12-15  epilogue: tcgen05.ld of each block's accumulator, FP32 register sums, partial sums out per segment
+//   WG3  warps 12-15  epilogue: tcgen05.ld of each block's accumulator, FP32 register sums, partial sums out per unit
+//
+// Store modes (the hand-over of a shared-memory stage from the TMA stores that read it to the TMA gathers that refill it
+// is where this kernel has an open fault).  Default: the store thread releases the stage after cp.async.bulk.wait_group.read — fast,
+// faults rarely under host contention.  OLFNAV_F2_STORE_SYNC=1: full completion wait after every block; =2: the stage is released
+// one block later; OLFNAV_F2_STORE_MODE=1: the transform warps store their own 32 rows and wait.  The three safe variants write
+// the same rows and cost 11-15 %.
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
